@@ -1,0 +1,97 @@
+"""ctypes binding of libhsenet_sm100a.so (C ABI in include/hsenet_b200.h).
+
+There is deliberately no CPU or eager-PyTorch fallback: if the shared library is missing the import of any
+compute entry point raises, and every non-zero status code from the library is turned into an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsenet_sm100a.so")
+
+OK = 0
+ERR_SHAPE, ERR_ALIGN, ERR_CUDA, ERR_ARG, ERR_DRIVER = -1, -2, -3, -4, -5
+PREC_BF16, PREC_FP32_VERIFY = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+
+vp = C.c_void_p
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("w_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+                                  "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [("stage", C.c_int32), ("num_layers", C.c_int32)] + [
+        (n, vp) for n in ("cls_token", "pos_embed", "w_patch", "b_patch", "blocks_host", "norm_g", "norm_b",
+                          "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score")]
+
+
+class PackerWeights(C.Structure):
+    _fields_ = [("out_dim", C.c_int32)] + [
+        (n, vp) for n in ("w_q", "b_q", "w_kv", "b_kv", "w_o", "b_o", "ln_g", "ln_b", "w_p0", "b_p0", "w_p2", "b_p2")]
+
+
+# name -> (restype, argtypes); mirrors include/hsenet_b200.h one to one (tests/test_abi.py checks the header).
+SIGNATURES = {
+    "hsenet_version": (C.c_char_p, []),
+    "hsenet_error_string": (C.c_char_p, [C.c_int]),
+    "hsenet_launch_count": (C.c_uint64, []),
+    "hsenet_vit_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hsenet_vit_forward": (C.c_int, [C.POINTER(VitWeights), vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp,
+                                     C.c_size_t, vp]),
+    "hsenet_packer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hsenet_packer_forward": (C.c_int, [C.POINTER(PackerWeights), vp, C.c_int, C.c_int, vp, C.c_int, C.c_int,
+                                        C.c_int, vp, C.c_size_t, vp]),
+    "hsenet_clip_image_head": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
+    "hsenet_linear": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
+                                vp, C.c_int, vp, C.c_int, C.c_int, vp]),
+    "hsenet_self_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "hsenet_layernorm": (C.c_int, [vp, vp, vp, C.c_long, vp, C.c_int, vp]),
+    "hsenet_patch_im2col": (C.c_int, [vp, C.c_int, vp, C.c_int, vp]),
+    "hsenet_packer_pool": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
+    "hsenet_packer_window_attention": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
+    "hsenet_slice_cross_attention": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp]),
+    "hsenet_slice_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "hsenet_gather_rows": (C.c_int, [vp, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "hsenet_patch_gather_map": (C.c_int, [vp, vp]),
+    "hsenet_packer_window_map": (C.c_int, [vp, vp]),
+    "hsenet_cast_bf16": (C.c_int, [vp, vp, C.c_long, vp]),
+}
+
+_lib = None
+
+
+class HSENetLibraryError(ImportError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise HSENetLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m hsenet_b200.build` (nvcc, sm_100a). "
+            "hsenet_b200 has no CPU / eager fallback by design.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here == ABI drift, surfaced at load time
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == OK:
+        return
+    msg = load().hsenet_error_string(rc).decode()
+    text = f"hsenet_b200 {what}: {msg} (code {rc})"
+    if rc in (ERR_SHAPE, ERR_ARG):
+        raise ValueError(text)
+    raise RuntimeError(text)

@@ -1,0 +1,96 @@
+// hsenet_b200 -- internal launcher prototypes shared by the .cu files (the public C ABI is include/hsenet_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hsenet_b200.h"
+
+namespace hs {
+
+enum : int {
+  HS_OK = HSENET_OK,
+  HS_ERR_SHAPE = HSENET_ERR_SHAPE,
+  HS_ERR_ALIGN = HSENET_ERR_ALIGN,
+  HS_ERR_CUDA = HSENET_ERR_CUDA,
+  HS_ERR_ARG = HSENET_ERR_ARG,
+  HS_ERR_DRIVER = HSENET_ERR_DRIVER,
+};
+
+// Fused GEMM epilogue:   v = acc + bias[col] (+ row_add[row % rows_per_group, col]) (+ resid[orow, col]);
+//                        v = gelu(v) if gelu;  out_f32[orow, col] = v;  out_act[orow, col] = (Act)v
+// orow = row, or (row / rows_per_group) * group_stride + group_offset + row % rows_per_group when rows_per_group>0.
+// `out_act` is bf16 for the tcgen05 GEMM and fp32 for the fp32 verification GEMM.
+struct GemmEpilogue {
+  const float* bias = nullptr;
+  const float* row_add = nullptr;   // [rows_per_group, N] fp32 (positional embedding)
+  const float* resid = nullptr;     // fp32, indexed by orow; may alias out_f32
+  int ld_resid = 0;
+  float* out_f32 = nullptr;
+  int ld_f32 = 0;
+  __nv_bfloat16* out_bf16 = nullptr;  // "out_act"
+  int ld_bf16 = 0;
+  int gelu = 0;
+  int rows_per_group = 0;
+  int group_stride = 0;
+  int group_offset = 0;
+};
+
+int num_sms();
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                      uint32_t box_inner, uint32_t box_outer);
+
+// ---- dense contractions -------------------------------------------------------------------------------------
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+              cudaStream_t stream);
+// fp32 verification GEMM (CUDA cores, fp32 operands and accumulation); ep.out_bf16 is reinterpreted as float*.
+int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+             cudaStream_t stream);
+
+// ---- self attention over the 3D token sequence (MONAI SABlock core) --------------------------------------------
+// qkv [B*S, 2304] with feature order (qkv, head, d); out [B*S, 768] heads concatenated.
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, cudaStream_t stream);
+int attention_f32(const float* qkv, float* out, int B, int S, cudaStream_t stream);
+
+// ---- row kernels ------------------------------------------------------------------------------------------------
+template <typename OutT>
+int layernorm_rows(const float* x, long ldx, const float* gamma, const float* beta, long rows, OutT* out, long ldo,
+                   OutT* out2_patch_only, int seq, cudaStream_t stream);
+template <typename OutT>
+int im2col_patches(const float* vol, int B, OutT* out, cudaStream_t stream);
+template <typename OutT>
+int cast_rows(const float* in, OutT* out, long n, cudaStream_t stream);
+int write_cls_rows(float* X, const float* cls, int B, int seq, cudaStream_t stream);
+// gather arbitrary-strided [B, rows, 768] (fp32 / bf16 / fp16 tagged by dtype code) into contiguous Act rows
+template <typename OutT>
+int gather_rows(const void* in, int in_dtype, long batch_stride, long row_stride, int B, int rows, OutT* out,
+                cudaStream_t stream);
+
+// ---- 2E3 slice-guided scoring (vit.py:332-345) ------------------------------------------------------------------
+// Q [B*2048,768] fp32 (projected query), KV [B*32,1536] fp32 (Wk|Wv of the slice features) -> O Act [B*2048,768]
+template <typename OutT>
+int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn_opt, int B, cudaStream_t stream);
+// Z = Wq(x)+out_proj(...) [B*2048,768] fp32 -> LN -> . w_s + b_s -> sigmoid -> X[b,1+t,:] = XP[b,t,:] * score
+int score_and_scale(const float* Z, const float* ln_g, const float* ln_b, const float* w_s, const float* b_s,
+                    const float* XP, float* X, float* scores_opt, int B, cudaStream_t stream);
+
+// ---- spatial packer (spatial_pooling_projector.py:121-153) -----------------------------------------------------------
+template <typename T>
+int packer_pool(const T* HR, T* LR, int B, cudaStream_t stream);
+// Q [B*128,768] fp32; KV [B*2048,1536] Act (Wk|Wv of the HR tokens, natural token order) -> O Act [B*128,768]
+template <typename T>
+int packer_window_attention(const float* Q, const T* KV, T* O, int B, cudaStream_t stream);
+
+// ---- CLIP head (CLIP_stage1.py:100-101,117) ------------------------------------------------------------------------
+int l2_normalize_rows(const float* in, float* out, int rows, int dim, cudaStream_t stream);
+
+// ---- 2D slice extraction (vit.py:529-531) ---------------------------------------------------------------------------
+template <typename OutT>
+int slice_extract(const float* vol, OutT* out, int B, int out_h, int out_w, cudaStream_t stream);
+
+// integer maps (device-computed, for bit-exact tests against the oracle's closed forms)
+int patch_gather_map(int32_t* out, cudaStream_t stream);      // [2048,1024]
+int packer_window_map(int32_t* out, cudaStream_t stream);     // [128,16]
+
+}  // namespace hs

@@ -1,0 +1,160 @@
+"""Host-side plumbing shared by the module facades: precision mode, device workspaces, weight cache.
+
+PyTorch is used here only for device memory, streams and dtype bookkeeping; all arithmetic of the hot path happens
+inside libhsenet_sm100a.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Iterable, Tuple
+
+import torch
+
+from . import _lib
+
+_PRECISIONS = {"bf16": _lib.PREC_BF16, "fp32_verify": _lib.PREC_FP32_VERIFY}
+_state = threading.local()
+_default_precision = os.environ.get("HSENET_B200_PRECISION", "bf16")
+
+
+def set_precision(name: str) -> None:
+    """'bf16' (tcgen05 tensor-core kernels, the product path) or 'fp32_verify' (fp32 CUDA-core verification mode)."""
+    if name not in _PRECISIONS:
+        raise ValueError(f"unknown precision {name!r}; expected one of {sorted(_PRECISIONS)}")
+    global _default_precision
+    _default_precision = name
+
+
+def get_precision() -> str:
+    return getattr(_state, "override", None) or _default_precision
+
+
+class precision:
+    """Context manager: ``with hsenet_b200.precision('fp32_verify'): ...``"""
+
+    def __init__(self, name: str):
+        if name not in _PRECISIONS:
+            raise ValueError(f"unknown precision {name!r}")
+        self.name = name
+
+    def __enter__(self):
+        self.prev = getattr(_state, "override", None)
+        _state.override = self.name
+        return self
+
+    def __exit__(self, *exc):
+        _state.override = self.prev
+        return False
+
+
+def precision_code(name: str | None = None) -> int:
+    return _PRECISIONS[name or get_precision()]
+
+
+def act_dtype(name: str | None = None) -> torch.dtype:
+    return torch.bfloat16 if (name or get_precision()) == "bf16" else torch.float32
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return _lib.DTYPE_F32
+    if dt == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    if dt == torch.float16:
+        return _lib.DTYPE_F16
+    raise ValueError(f"unsupported dtype {dt}")
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"hsenet_b200: {what} must live on a CUDA device (got {t.device}); there is no CPU path. "
+            "Move the module and its inputs to cuda.")
+
+
+def forbid_autograd(params: Iterable[torch.Tensor], what: str) -> None:
+    """Forward-only in this round (SURVEY.md section 8 row f-1 is the backward)."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        raise NotImplementedError(
+            f"hsenet_b200.{what}: backward is not implemented yet; run under torch.no_grad() / inference_mode() "
+            "or freeze the module with requires_grad_(False).")
+
+
+# ---- workspaces: one growing buffer per (device, tag); reused across calls on the same stream ---------------------
+_workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def workspace(device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _workspaces.pop(key, None)
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+# ---- weight cache ----------------------------------------------------------------------------------------------------
+def _sig(params) -> tuple:
+    return tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params)
+
+
+def cast_weight(w: torch.Tensor, prec: str) -> torch.Tensor:
+    """Matrix operand in the act dtype ([out,in] row-major, exactly as nn.Linear stores it)."""
+    w = w.detach()
+    if prec == "bf16":
+        if w.dtype == torch.bfloat16:
+            return w.contiguous()
+        src = w.float().contiguous()
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+        _lib.check(_lib.load().hsenet_cast_bf16(src.data_ptr(), out.data_ptr(), src.numel(), stream_ptr(src.device)),
+                   "cast_bf16")
+        return out
+    return w.float().contiguous()
+
+
+def f32(p: torch.Tensor) -> torch.Tensor:
+    return p.detach().float().contiguous()
+
+
+class WeightCache:
+    """Derived (packed / down-cast) copies of a module's parameters, rebuilt when any parameter's storage or
+    version counter changes (load_state_dict, optimizer step, .to())."""
+
+    def __init__(self):
+        self.sig = None
+        self.prec = None
+        self.payload = None
+
+    def __deepcopy__(self, memo):
+        return WeightCache()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def get(self, params, prec: str, builder):
+        params = list(params)
+        sig = _sig(params)
+        if self.payload is None or sig != self.sig or prec != self.prec:
+            self.payload = builder(prec)
+            self.sig = sig
+            self.prec = prec
+        return self.payload
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,338 @@
+"""Module facades for the 3D vision encoders, drop-in for the reference's
+``Preprint/LaMed/src/model/multimodal_encoder/vit.py`` live classes:
+
+    regular_attention          (vit.py:36-64)     parameter container of the slice-guided cross attention
+    ViT_stage1                 (vit.py:360-469)   3D ViT ("3D Vision Encoder")
+    ViT_stage2                 (vit.py:222-357)   2E3 encoder (3D ViT gated by 32 slice features)
+    ViT3DTower_dual_encoders   (vit.py:891-960)   tower wrapper used by build_vision_tower
+
+Constructor / forward signatures, attribute names, parameter names, shapes and *registration order* follow the
+reference (and the MONAI 1.3.0 blocks it is assembled from), so ``state_dict()`` round-trips with reference
+checkpoints and with the positional weight copy in train/train_VLM.py:477-503 (138 / 150 keys).
+The modules hold parameters only; ``forward`` runs entirely inside libhsenet_sm100a.so (hsenet_vit_forward).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import runtime as rt
+
+IMG_SIZE = (32, 256, 256)
+PATCH_SIZE = (4, 16, 16)
+N_PATCH = 2048
+SEQ = 2049
+HIDDEN = 768
+MLP_DIM = 3072
+HEADS = 12
+PATCH_DIM = 1024
+
+
+# ---- parameter containers named like the MONAI 1.3.0 blocks the reference instantiates (vit.py:290-305) ----------
+class PatchRearrange(nn.Module):
+    """Index 0 of ``patch_embeddings`` (MONAI puts an einops Rearrange there; it owns no parameters).  Called on its
+    own it runs the CUDA im2col: [B,1,32,256,256] -> [B,2048,1024]."""
+
+    def forward(self, x):
+        rt.require_cuda(x, "images")
+        x = x.float().contiguous()
+        out = torch.empty(x.shape[0], N_PATCH, PATCH_DIM, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().hsenet_patch_im2col(x.data_ptr(), x.shape[0], out.data_ptr(), _lib.DTYPE_F32,
+                                                   rt.stream_ptr(x.device)), "patch_im2col")
+        return out
+
+
+class PatchEmbeddingBlock(nn.Module):
+    def __init__(self, in_channels, img_size, patch_size, hidden_size, num_heads, pos_embed, dropout_rate=0.0,
+                 spatial_dims=3):
+        super().__init__()
+        if pos_embed != "perceptron":
+            raise ValueError("hsenet_b200 implements the reference's pos_embed='perceptron' patch embedding only")
+        self.n_patches = N_PATCH
+        self.patch_dim = PATCH_DIM
+        self.patch_embeddings = nn.Sequential(PatchRearrange(), nn.Linear(PATCH_DIM, hidden_size))
+        self.position_embeddings = nn.Parameter(torch.zeros(1, N_PATCH, hidden_size))
+        nn.init.trunc_normal_(self.position_embeddings, mean=0.0, std=0.02, a=-2.0, b=2.0)
+        nn.init.trunc_normal_(self.patch_embeddings[1].weight, mean=0.0, std=0.02, a=-2.0, b=2.0)
+        nn.init.constant_(self.patch_embeddings[1].bias, 0)
+
+
+class MLPBlock(nn.Module):
+    def __init__(self, hidden_size, mlp_dim):
+        super().__init__()
+        self.linear1 = nn.Linear(hidden_size, mlp_dim)
+        self.linear2 = nn.Linear(mlp_dim, hidden_size)
+
+
+class SABlock(nn.Module):
+    def __init__(self, hidden_size, num_heads, qkv_bias=False):
+        super().__init__()
+        self.num_heads = num_heads
+        self.out_proj = nn.Linear(hidden_size, hidden_size)
+        self.qkv = nn.Linear(hidden_size, hidden_size * 3, bias=qkv_bias)
+
+
+class TransformerBlock(nn.Module):
+    """Children registered in MONAI's order: mlp, norm1, attn, norm2."""
+
+    def __init__(self, hidden_size, mlp_dim, num_heads, dropout_rate=0.0, qkv_bias=False, save_attn=False):
+        super().__init__()
+        self.mlp = MLPBlock(hidden_size, mlp_dim)
+        self.norm1 = nn.LayerNorm(hidden_size)
+        self.attn = SABlock(hidden_size, num_heads, qkv_bias)
+        self.norm2 = nn.LayerNorm(hidden_size)
+
+
+class regular_attention(nn.Module):
+    """Parameter container with the reference's names (vit.py:36-49); the arithmetic of ``forward`` (vit.py:50-64)
+    is fused into hsenet_vit_forward for stage 2.  The two Dropout(p=0.1) members are inactive in eval; training
+    mode is rejected by the parent module."""
+
+    def __init__(self, in_channels=16, out_channels=8, emb_dim=768, output_dim=768, dropout=0.1, aropout=0.0):
+        super().__init__()
+        self.emb_dim = emb_dim
+        self.Wq = nn.Linear(emb_dim, emb_dim)
+        self.Wk = nn.Linear(emb_dim, emb_dim)
+        self.Wv = nn.Linear(emb_dim, emb_dim)
+        self.attn = None
+        self.output_linear = nn.Linear(emb_dim, emb_dim)
+        self.dropout = nn.Dropout(p=dropout)
+        self.dropout_2 = nn.Dropout(p=dropout)
+        self.norm = nn.LayerNorm(emb_dim)
+
+
+def _check_geometry(in_channels, img_size, patch_size, hidden_size, mlp_dim, num_heads, dropout_rate, spatial_dims,
+                    qkv_bias):
+    if not (0 <= dropout_rate <= 1):
+        raise ValueError("dropout_rate should be between 0 and 1.")
+    if hidden_size % num_heads != 0:
+        raise ValueError("hidden_size should be divisible by num_heads.")
+    img = tuple(img_size) if isinstance(img_size, Sequence) else (img_size,) * spatial_dims
+    pat = tuple(patch_size) if isinstance(patch_size, Sequence) else (patch_size,) * spatial_dims
+    if (in_channels, img, pat, hidden_size, mlp_dim, num_heads, spatial_dims) != (
+            1, IMG_SIZE, PATCH_SIZE, HIDDEN, MLP_DIM, HEADS, 3):
+        raise ValueError(
+            "hsenet_b200 supports the reference's shipped geometry only: in_channels=1, img_size=(32,256,256), "
+            "patch_size=(4,16,16), hidden_size=768, mlp_dim=3072, num_heads=12 "
+            "(the packer hard-codes it, spatial_pooling_projector.py:140)")
+    if dropout_rate != 0.0:
+        raise ValueError("hsenet_b200: dropout_rate must be 0.0 (every reference config uses 0.0)")
+    if qkv_bias:
+        raise ValueError("hsenet_b200: qkv_bias=True is not supported (reference passes False)")
+
+
+class _ViTBase(nn.Module):
+    """Shared machinery of ViT_stage1 / ViT_stage2."""
+
+    _stage = 1
+
+    def _init_common(self, in_channels, img_size, patch_size, hidden_size, mlp_dim, num_layers, num_heads, pos_embed,
+                     classification, dropout_rate, spatial_dims, qkv_bias, save_attn):
+        _check_geometry(in_channels, img_size, patch_size, hidden_size, mlp_dim, num_heads, dropout_rate,
+                        spatial_dims, qkv_bias)
+        self.hidden_size = hidden_size
+        self.classification = classification
+        self.patch_embedding = PatchEmbeddingBlock(in_channels, img_size, patch_size, hidden_size, num_heads,
+                                                   pos_embed, dropout_rate, spatial_dims)
+        self.blocks = nn.ModuleList(
+            [TransformerBlock(hidden_size, mlp_dim, num_heads, dropout_rate, qkv_bias, save_attn)
+             for _ in range(num_layers)])
+
+    def _finish_init(self):
+        #: set True to materialise the per-block hidden states (2nd return value, vit.py:463-466); the live callers
+        #: discard them, so by default an empty list is returned and 12 x [B,2049,768] copies are skipped.
+        self.return_hidden_states = False
+        #: dtype of the returned features; None = the activation dtype of the precision mode (bf16 / fp32)
+        self.output_dtype = None
+        self.last_patch_tokens = None
+        self.last_scores = None
+        self._cache = rt.WeightCache()
+
+    # -- weights -> C struct ---------------------------------------------------------------------------------------
+    def _build_payload(self, prec: str):
+        cw = lambda w: rt.cast_weight(w, prec)
+        keep = []
+
+        def k(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        n = len(self.blocks)
+        blocks = (_lib.BlockWeights * max(n, 1))()
+        for i, blk in enumerate(self.blocks):
+            b = blocks[i]
+            b.w_qkv = k(cw(blk.attn.qkv.weight))
+            b.w_out = k(cw(blk.attn.out_proj.weight)); b.b_out = k(rt.f32(blk.attn.out_proj.bias))
+            b.w_fc1 = k(cw(blk.mlp.linear1.weight)); b.b_fc1 = k(rt.f32(blk.mlp.linear1.bias))
+            b.w_fc2 = k(cw(blk.mlp.linear2.weight)); b.b_fc2 = k(rt.f32(blk.mlp.linear2.bias))
+            b.ln1_g = k(rt.f32(blk.norm1.weight)); b.ln1_b = k(rt.f32(blk.norm1.bias))
+            b.ln2_g = k(rt.f32(blk.norm2.weight)); b.ln2_b = k(rt.f32(blk.norm2.bias))
+        w = _lib.VitWeights()
+        w.stage = self._stage
+        w.num_layers = n
+        dev = self.norm.weight.device
+        cls = self.cls_token if hasattr(self, "cls_token") else torch.zeros(1, 1, HIDDEN, device=dev)
+        w.cls_token = k(rt.f32(cls).reshape(-1))
+        w.pos_embed = k(rt.f32(self.patch_embedding.position_embeddings).reshape(N_PATCH, HIDDEN))
+        lin = self.patch_embedding.patch_embeddings[1]
+        w.w_patch = k(cw(lin.weight)); w.b_patch = k(rt.f32(lin.bias))
+        w.blocks_host = C.cast(blocks, C.c_void_p)
+        w.norm_g = k(rt.f32(self.norm.weight)); w.norm_b = k(rt.f32(self.norm.bias))
+        if self._stage == 2:
+            a = self.slice_guided_attention
+            w.w_sq = k(cw(a.Wq.weight)); w.b_sq = k(rt.f32(a.Wq.bias))
+            w.w_skv = k(cw(torch.cat([a.Wk.weight.detach(), a.Wv.weight.detach()], 0)))
+            w.b_skv = k(torch.cat([rt.f32(a.Wk.bias), rt.f32(a.Wv.bias)], 0))
+            w.w_so = k(cw(a.output_linear.weight)); w.b_so = k(rt.f32(a.output_linear.bias))
+            w.sn_g = k(rt.f32(a.norm.weight)); w.sn_b = k(rt.f32(a.norm.bias))
+            w.w_score = k(rt.f32(self.patch_score_proj.weight).reshape(-1))
+            w.b_score = k(rt.f32(self.patch_score_proj.bias).reshape(-1))
+        return {"struct": w, "blocks": blocks, "keep": keep}
+
+    def _run(self, x, image_2d):
+        rt.require_cuda(x, "images")
+        rt.require_cuda(self.norm.weight, f"{type(self).__name__} parameters")
+        rt.forbid_autograd(self.parameters(), type(self).__name__)
+        if x.dim() != 5 or tuple(x.shape[1:]) != (1,) + IMG_SIZE:
+            raise ValueError(f"expected images of shape [B,1,32,256,256], got {tuple(x.shape)}")
+        dev = x.device
+        B = x.shape[0]
+        prec = rt.get_precision()
+        payload = self._cache.get(self.parameters(), prec, self._build_payload)
+        lib = _lib.load()
+        act = rt.act_dtype(prec)
+        xin = x.detach().float().contiguous()                 # reference clones its input (vit.py:455)
+        s2d = None
+        if self._stage == 2:
+            if image_2d is None:
+                raise ValueError("ViT_stage2.forward needs image_2d [B,32,768]")
+            s2d = image_2d.detach().to(dev).reshape(B, 32, -1).float().contiguous()   # vit.py:332
+            if s2d.shape[-1] != HIDDEN:
+                raise ValueError(f"image_2d must reshape to [B,32,768], got {tuple(image_2d.shape)}")
+        tokens = torch.empty(B, SEQ, HIDDEN, dtype=act, device=dev)
+        patch = torch.empty(B, N_PATCH, HIDDEN, dtype=act, device=dev)
+        hidden = None
+        if self.return_hidden_states and len(self.blocks) > 0:
+            hidden = torch.empty(len(self.blocks), B, SEQ, HIDDEN, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, N_PATCH, dtype=torch.float32, device=dev) if self._stage == 2 else None
+        pc = rt.precision_code(prec)
+        nbytes = lib.hsenet_vit_workspace_bytes(B, pc, self._stage)
+        ws = rt.workspace(dev, nbytes, "vit")
+        with torch.cuda.device(dev):
+            rc = lib.hsenet_vit_forward(C.byref(payload["struct"]), xin.data_ptr(), rt.ptr(s2d), B, pc,
+                                        tokens.data_ptr(), patch.data_ptr(), rt.ptr(hidden), rt.ptr(scores),
+                                        ws.data_ptr(), ws.numel(), rt.stream_ptr(dev))
+        _lib.check(rc, f"vit_forward(stage={self._stage})")
+        self.last_patch_tokens = patch
+        self.last_scores = scores
+        if self.output_dtype is not None and self.output_dtype != act:
+            tokens = tokens.to(self.output_dtype)
+            self.last_patch_tokens = patch.to(self.output_dtype)
+        hs = [] if hidden is None else [h.to(tokens.dtype) for h in hidden.unbind(0)]
+        return tokens, hs
+
+
+class ViT_stage1(_ViTBase):
+    """3D Vision Encoder.  Same constructor as the reference (vit.py:368-385); ``forward`` returns
+    ``(x [B,2049,768], hidden_states)`` like vit.py:449-469."""
+
+    _stage = 1
+
+    def __init__(self, in_channels: int, img_size, patch_size, hidden_size: int = 768, mlp_dim: int = 3072,
+                 num_layers: int = 12, num_heads: int = 12, pos_embed: str = "conv", classification: bool = False,
+                 num_classes: int = 2, dropout_rate: float = 0.0, spatial_dims: int = 3, post_activation="Tanh",
+                 qkv_bias: bool = False, save_attn: bool = False) -> None:
+        super().__init__()
+        self._init_common(in_channels, img_size, patch_size, hidden_size, mlp_dim, num_layers, num_heads, pos_embed,
+                          classification, dropout_rate, spatial_dims, qkv_bias, save_attn)
+        self.norm = nn.LayerNorm(hidden_size)
+        if self.classification:
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, hidden_size))
+        else:
+            raise ValueError("hsenet_b200: classification=True (cls token) is what every reference caller uses")
+        self._finish_init()
+
+    def forward(self, x, k=None, visual_encoder_2D=None, text_features=None, image_path=None):
+        return self._run(x, None)
+
+
+class ViT_stage2(_ViTBase):
+    """2E3 encoder.  Same constructor as the reference (vit.py:230-247); ``forward(x, image_2d, ...)`` returns
+    ``(x_weighted [B,2049,768], hidden_states)`` like vit.py:315-357."""
+
+    _stage = 2
+
+    def __init__(self, in_channels: int, img_size, patch_size, hidden_size: int = 768, mlp_dim: int = 3072,
+                 num_layers: int = 12, num_heads: int = 12, pos_embed: str = "conv", classification: bool = False,
+                 num_classes: int = 2, dropout_rate: float = 0.0, spatial_dims: int = 3, post_activation="Tanh",
+                 qkv_bias: bool = False, save_attn: bool = False) -> None:
+        super().__init__()
+        self._init_common(in_channels, img_size, patch_size, hidden_size, mlp_dim, num_layers, num_heads, pos_embed,
+                          classification, dropout_rate, spatial_dims, qkv_bias, save_attn)
+        self.patch_score_proj = nn.Linear(hidden_size, 1)
+        self.patch_score_norm = nn.Sigmoid()
+        self.slice_guided_attention = regular_attention()
+        self.norm = nn.LayerNorm(hidden_size)
+        if self.classification:
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, hidden_size))
+        else:
+            raise ValueError("hsenet_b200: classification=True (cls token) is what every reference caller uses")
+        self._finish_init()
+
+    def forward(self, x, image_2d, k=None, visual_encoder_2D=None, text_features=None, image_path=None):
+        if self.training and self.slice_guided_attention.dropout.p > 0:
+            raise NotImplementedError(
+                "ViT_stage2 in .train() mode applies Dropout(p=0.1) inside slice_guided_attention (vit.py:46-47); "
+                "hsenet_b200 implements the eval-mode forward only -- call .eval()")
+        return self._run(x, image_2d)
+
+
+class ViT3DTower_dual_encoders(nn.Module):
+    """Tower wrapper, drop-in for vit.py:891-960 (built by build_vision_tower for
+    ``config.vision_tower == 'vit_stage2_dual_encoders'``)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.select_layer = config.vision_select_layer
+        self.select_feature = config.vision_select_feature
+        self.remain_2d3d_ViT_type = getattr(config, "remain_2d3d_ViT_type", "dual_vits")
+        kw = dict(in_channels=self.config.image_channel, img_size=self.config.image_size,
+                  patch_size=self.config.patch_size, pos_embed="perceptron",
+                  spatial_dims=len(self.config.patch_size), classification=True)
+        self.vision_tower_stage1 = ViT_stage1(**kw)
+        self.vision_tower_stage2 = ViT_stage2(**kw)
+
+    def forward(self, images, images_2d):
+        t = self.remain_2d3d_ViT_type
+        if self.select_feature not in ("patch", "cls_patch"):
+            raise ValueError(f"Unexpected select feature: {self.select_feature}")
+        feats = []
+        # the reference always runs both encoders (vit.py:928-929); skipping the unused one changes no result
+        if t in ("dual_vits", "3d_vit"):
+            tok, _ = self.vision_tower_stage1(images)
+            feats.append(self.vision_tower_stage1.last_patch_tokens if self.select_feature == "patch" else tok)
+        if t in ("dual_vits", "2e3_vit"):
+            tok, _ = self.vision_tower_stage2(images, images_2d)
+            feats.append(self.vision_tower_stage2.last_patch_tokens if self.select_feature == "patch" else tok)
+        if t == "dual_vits":
+            return feats[0], feats[1]
+        if t in ("3d_vit", "2e3_vit"):
+            return feats[0]
+        return None
+
+    @property
+    def dtype(self):
+        return self.vision_tower_stage1.norm.weight.dtype
+
+    @property
+    def device(self):
+        return self.vision_tower_stage1.norm.weight.device
+
+    @property
+    def hidden_size(self):
+        return self.vision_tower_stage1.hidden_size

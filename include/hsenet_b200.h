@@ -1,0 +1,186 @@
+/* hsenet_b200.h -- C ABI of libhsenet_sm100a.so: the B200-native HSENet visual-encoding hot path.
+ *
+ * The reference (YanzhaoShi/HSENet) has no FFI layer: its seam is Python nn.Module duck typing
+ * (Preprint/LaMed/src/model/multimodal_encoder/builder.py:4-11, multimodal_projector/builder.py:81-105).  The
+ * Python facades in hsenet_b200/ keep those module signatures and call the entry points below through ctypes;
+ * any other host (C++, Go/cgo, Rust FFI ...) can bind the same symbols.  Each entry point names the reference
+ * code it replaces (paths relative to Preprint/LaMed/src/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - no allocation, no synchronisation, no global mutable state: workspaces are caller-allocated
+ *     (size from the *_workspace_bytes functions), calls are asynchronous on `stream`;
+ *   - return value: HSENET_OK or a negative HSENET_ERR_* code (bad shape / misaligned pointer / CUDA launch
+ *     failure).  Nothing aborts; there is no CPU fallback.
+ *   - geometry is the one the reference hard-codes: volume 1x32x256x256, patch 4x16x16 -> 8x16x16 = 2048 tokens
+ *     (+1 cls), hidden 768, 12 heads x 64, MLP 3072 (model/multimodal_projector/spatial_pooling_projector.py:140,
+ *     model/lamed_arch.py:125, model/multimodal_encoder/vit.py:437).
+ *   - precision: HSENET_PREC_BF16 = bf16 tensor-core kernels (tcgen05) with fp32 accumulation, fp32 residual
+ *     stream and fp32 LayerNorm/softmax statistics; weights are bf16 copies ([out,in] row-major, as nn.Linear
+ *     stores them), biases / LayerNorm / positional parameters stay fp32.
+ *     HSENET_PREC_FP32_VERIFY = the same pipeline with fp32 operands and fp32 accumulation on CUDA cores
+ *     (the north-star "fp32-accumulate verification mode", tolerance 1e-4); weights are the fp32 parameters.
+ *     "act" below means bf16 in BF16 mode and fp32 in FP32_VERIFY mode.
+ */
+#ifndef HSENET_B200_H
+#define HSENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSENET_OK 0
+#define HSENET_ERR_SHAPE (-1)  /* unsupported dimension (e.g. N not a multiple of 256) */
+#define HSENET_ERR_ALIGN (-2)  /* pointer or leading dimension not 16-byte aligned */
+#define HSENET_ERR_CUDA (-3)   /* kernel launch failed (cudaGetLastError) */
+#define HSENET_ERR_ARG (-4)    /* null pointer / bad enum / workspace too small */
+#define HSENET_ERR_DRIVER (-5) /* cuTensorMapEncodeTiled unavailable or failed */
+
+#define HSENET_PREC_BF16 0
+#define HSENET_PREC_FP32_VERIFY 1
+
+#define HSENET_DTYPE_F32 0
+#define HSENET_DTYPE_BF16 1
+#define HSENET_DTYPE_F16 2
+
+typedef void* hsenet_stream_t;
+
+/* One MONAI TransformerBlock (constructed at vit.py:438-443).  w_* are act-typed [out,in]; the rest fp32. */
+typedef struct hsenet_block_weights {
+  const void* w_qkv;   /* attn.qkv.weight      [2304,768], no bias (qkv_bias=False, vit.py:440) */
+  const void* w_out;   /* attn.out_proj.weight [768,768]  */
+  const float* b_out;  /* attn.out_proj.bias   [768]      */
+  const void* w_fc1;   /* mlp.linear1.weight   [3072,768] */
+  const float* b_fc1;
+  const void* w_fc2;   /* mlp.linear2.weight   [768,3072] */
+  const float* b_fc2;
+  const float* ln1_g;  /* norm1 */
+  const float* ln1_b;
+  const float* ln2_g;  /* norm2 */
+  const float* ln2_b;
+} hsenet_block_weights;
+
+/* ViT_stage1 (vit.py:360-469) when stage == 1, ViT_stage2 (vit.py:222-357) when stage == 2. */
+typedef struct hsenet_vit_weights {
+  int32_t stage;       /* 1 or 2 */
+  int32_t num_layers;  /* 12 in every shipped config */
+  const float* cls_token;                  /* [768]       cls_token (vit.py:447)                         */
+  const float* pos_embed;                  /* [2048,768]  patch_embedding.position_embeddings            */
+  const void* w_patch;                     /* [768,1024]  patch_embedding.patch_embeddings.1.weight      */
+  const float* b_patch;                    /* [768]                                                      */
+  const hsenet_block_weights* blocks_host; /* HOST array of num_layers entries                           */
+  const float* norm_g;                     /* final LayerNorm (vit.py:445)                               */
+  const float* norm_b;
+  /* stage 2 only: slice_guided_attention = regular_attention (vit.py:36-64) + patch_score_proj (vit.py:308) */
+  const void* w_sq;    /* Wq.weight [768,768] */
+  const float* b_sq;
+  const void* w_skv;   /* rows 0..767 = Wk.weight, rows 768..1535 = Wv.weight  -> [1536,768] */
+  const float* b_skv;  /* [1536] = Wk.bias | Wv.bias */
+  const void* w_so;    /* output_linear.weight [768,768] */
+  const float* b_so;
+  const float* sn_g;   /* slice_guided_attention.norm */
+  const float* sn_b;
+  const float* w_score; /* patch_score_proj.weight [768] */
+  const float* b_score; /* patch_score_proj.bias   [1]   */
+} hsenet_vit_weights;
+
+/* VisualPacker_3d_phi_v3 (spatial_pooling_projector.py:121-153). */
+typedef struct hsenet_packer_weights {
+  int32_t out_dim;     /* 3072 for Phi-4-mini; must be a multiple of 256 */
+  const void* w_q;     /* resolution_attention.Wq.weight [768,768] */
+  const float* b_q;
+  const void* w_kv;    /* Wk.weight | Wv.weight stacked -> [1536,768] */
+  const float* b_kv;
+  const void* w_o;     /* resolution_attention.output_linear.weight */
+  const float* b_o;
+  const float* ln_g;   /* resolution_attention.norm */
+  const float* ln_b;
+  const void* w_p0;    /* proj_mpls.0.weight [out_dim,768] */
+  const float* b_p0;
+  const void* w_p2;    /* proj_mpls.2.weight [out_dim,out_dim] */
+  const float* b_p2;
+} hsenet_packer_weights;
+
+const char* hsenet_version(void);
+const char* hsenet_error_string(int code);
+/* Number of kernels launched by this library in this process so far (bench.py's `gpu_launches`). */
+uint64_t hsenet_launch_count(void);
+
+/* ---- composite entry points ----------------------------------------------------------------------------------- */
+
+/* Replaces ViT_stage1.forward (vit.py:449-469) / ViT_stage2.forward (vit.py:315-357).
+ *   images      fp32 [B,1,32,256,256] contiguous
+ *   images_2d   fp32 [B,32,768] (stage 2 only; the pre-computed slice features, dataset/multi_dataset.py:357-362)
+ *   out_tokens  act  [B,2049,768]  final LayerNorm output (cls row first)            (may be NULL)
+ *   out_patch   act  [B,2048,768]  the same without the cls row, contiguous -- what
+ *               ViT3DTower_dual_encoders hands to the packer with select_feature == "patch" (vit.py:934-936) (may be NULL)
+ *   hidden_f32  fp32 [num_layers,B,2049,768] per-block outputs (the second return value, vit.py:463-466) (may be NULL)
+ *   scores_f32  fp32 [B,2048] sigmoid patch scores of stage 2 (vit.py:339)           (may be NULL)
+ */
+size_t hsenet_vit_workspace_bytes(int B, int precision, int stage);
+int hsenet_vit_forward(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B,
+                       int precision, void* out_tokens, void* out_patch, float* hidden_f32, float* scores_f32,
+                       void* workspace, size_t workspace_bytes, hsenet_stream_t stream);
+
+/* Replaces VisualPacker_3d_phi_v3.forward (spatial_pooling_projector.py:138-146) and the torch.cat of
+ * LamedMetaForCausalLM.encode_images (lamed_arch.py:132): writes packed token n of batch b to
+ *   out[(b * out_tokens_per_batch + token_offset + n) * out_dim + :],  n in [0,128).
+ *   hr   act [B,2048,768] contiguous (tower features without cls);  out_dtype HSENET_DTYPE_* of `out`
+ *   (BF16 mode: BF16 or F32; FP32_VERIFY: F32). */
+size_t hsenet_packer_workspace_bytes(int B, int precision, int out_dim);
+int hsenet_packer_forward(const hsenet_packer_weights* w, const void* hr, int B, int precision, void* out,
+                          int out_dtype, int out_tokens_per_batch, int token_offset, void* workspace,
+                          size_t workspace_bytes, hsenet_stream_t stream);
+
+/* Replaces the image half of M3DCLIP_stage1.encode_image + [:,0] (CLIP_stage1.py:100-101,117):
+ * out[b,:] = normalize(W * tokens[b,0,:] + bias)  -- only the cls row is projected (row 0 is numerically the
+ * same as projecting all 2049 rows and slicing).  tokens act [B,2049,768]; w_proj act [768,768]; out fp32 [B,768];
+ * workspace >= B*768*4 bytes. */
+int hsenet_clip_image_head(const void* tokens, const void* w_proj, const float* b_proj, int B, int precision,
+                           float* out, void* workspace, size_t workspace_bytes, hsenet_stream_t stream);
+
+/* ---- operator-level entry points (unit-tested individually; the composites are built from these) ------------- */
+
+/* out = epilogue(A[M,K] * W[N,K]^T): bias, optional exact-erf GELU, optional fp32 residual (may alias out_f32),
+ * fp32 and/or act outputs.  nn.Linear semantics (MONAI SABlock.qkv/out_proj, MLPBlock.linear1/2, ...). */
+int hsenet_linear(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                  const float* resid, int ld_resid, int gelu, float* out_f32, int ld_f32, void* out_act,
+                  int ld_act, int precision, hsenet_stream_t stream);
+/* MONAI SABlock core: softmax(q k^T / 8) v per head; qkv act [B*S,2304] in (qkv, head, d) order -> out act [B*S,768]. */
+int hsenet_self_attention(const void* qkv, void* out, int B, int S, int precision, hsenet_stream_t stream);
+/* nn.LayerNorm(768), eps 1e-5, fp32 statistics; x fp32 [rows,768] -> out (F32 or BF16). */
+int hsenet_layernorm(const float* x, const float* gamma, const float* beta, long rows, void* out, int out_dtype,
+                     hsenet_stream_t stream);
+/* MONAI PatchEmbeddingBlock rearrange (vit.py:437): images fp32 [B,1,32,256,256] -> out [B*2048,1024] (F32/BF16). */
+int hsenet_patch_im2col(const float* images, int B, void* out, int out_dtype, hsenet_stream_t stream);
+/* avg_pool3d kernel (1,4,4) over the 8x16x16 grid (spatial_pooling_projector.py:141): hr [B,2048,768] -> [B,128,768]. */
+int hsenet_packer_pool(const void* hr, void* lr, int B, int dtype, hsenet_stream_t stream);
+/* per-window single-head attention (spatial_pooling_projector.py:76 via :8-16): q fp32 [B*128,768],
+ * kv [B*2048,1536] (dtype) -> out [B*128,768] (dtype). */
+int hsenet_packer_window_attention(const float* q, const void* kv, void* out, int B, int dtype,
+                                   hsenet_stream_t stream);
+/* regular_attention core (vit.py:25-33,59): q fp32 [B*2048,768], kv fp32 [B*32,1536] -> out [B*2048,768] (dtype),
+ * optional attention map fp32 [B,2048,32]. */
+int hsenet_slice_cross_attention(const float* q, const float* kv, void* out, float* attn, int B, int dtype,
+                                 hsenet_stream_t stream);
+/* trilinear (32,256,256)->(32,out_h,out_w) + 3-channel expand + permute (vit.py:529-531):
+ * images fp32 [B,1,32,256,256] -> out [B*32,3,out_h,out_w] (F32/BF16). */
+int hsenet_slice_extract(const float* images, void* out, int B, int out_h, int out_w, int out_dtype,
+                         hsenet_stream_t stream);
+/* strided [B,rows,768] (any HSENET_DTYPE_*) -> contiguous [B*rows,768] (F32/BF16); strides in elements. */
+int hsenet_gather_rows(const void* in, int in_dtype, long batch_stride, long row_stride, int B, int rows,
+                       void* out, int out_dtype, hsenet_stream_t stream);
+/* integer maps computed on the device exactly as the kernels index memory (bit-exact parity tests). */
+int hsenet_patch_gather_map(int32_t* out /*[2048,1024]*/, hsenet_stream_t stream);
+int hsenet_packer_window_map(int32_t* out /*[128,16]*/, hsenet_stream_t stream);
+/* fp32 -> bf16 (round-to-nearest-even) cast used to build the weight cache. */
+int hsenet_cast_bf16(const float* in, void* out, long n, hsenet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSENET_B200_H */

@@ -1,0 +1,133 @@
+"""End-to-end parity (-m gpu): the module facades (through the C ABI) against the CPU oracle on identical synthetic
+volumes and shared random-init weights.  Tolerances are BASELINE.json's: bf16 cos >= 0.999 and
+max|err|/max|ref| <= 2e-2; fp32 verification mode <= 1e-4."""
+import pytest
+import torch
+
+from util import GEOM, O, assert_bf16, assert_fp32, cpu_state, metrics, randomize_params, synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(cls, layers, seed=0, **kw):
+    torch.manual_seed(seed)
+    m = cls(num_layers=layers, **GEOM, **kw) if layers is not None else cls(**kw)
+    return randomize_params(m).eval()
+
+
+@pytest.mark.parametrize("layers,B", [(2, 2), (12, 1)])
+def test_vit_stage1(cuda, layers, B):
+    import hsenet_b200 as H
+    m = _build(H.ViT_stage1, layers)
+    sd = cpu_state(m)
+    x, _ = synthetic_inputs(B)
+    ref, ref_h = O.vit_stage1(sd, x)
+    m = m.to(cuda)
+    m.return_hidden_states = True
+    with torch.no_grad():
+        with H.precision("fp32_verify"):
+            got, hs = m(x.to(cuda))
+        assert got.dtype == torch.float32 and got.shape == (B, 2049, 768) and len(hs) == layers
+        print("fp32_verify", assert_fp32(got, ref, "vit_stage1 fp32"))
+        assert_fp32(hs[0], ref_h[0], "hidden[0] fp32")
+        assert_fp32(m.last_patch_tokens, ref[:, 1:], "patch tokens fp32")
+        with H.precision("bf16"):
+            got, hs = m(x.to(cuda))
+        assert got.dtype == torch.bfloat16
+        print("bf16", assert_bf16(got, ref, "vit_stage1 bf16"))
+        assert_bf16(hs[-1], ref_h[-1], "hidden[-1] bf16")
+        assert torch.equal(m.last_patch_tokens, got[:, 1:])
+
+
+@pytest.mark.parametrize("layers,B", [(2, 2), (12, 1)])
+def test_vit_stage2(cuda, layers, B):
+    import hsenet_b200 as H
+    m = _build(H.ViT_stage2, layers, seed=1)
+    with torch.no_grad():    # make the gate informative: default init gives scores ~0.5 everywhere
+        m.patch_score_proj.weight.mul_(20.0)
+    sd = cpu_state(m)
+    x, s = synthetic_inputs(B, seed=77)
+    ref, _ = O.vit_stage2(sd, x, s)
+    ref_scores, _ = O.patch_scores(sd, O.patch_embedding(sd, x), s)
+    m = m.to(cuda)
+    with torch.no_grad():
+        with H.precision("fp32_verify"):
+            got, _ = m(x.to(cuda), s.to(cuda))
+        print("fp32_verify", assert_fp32(got, ref, "vit_stage2 fp32"))
+        assert_fp32(m.last_scores, ref_scores, "scores fp32")
+        with H.precision("bf16"):
+            got, _ = m(x.to(cuda), s.to(cuda))
+        print("bf16", assert_bf16(got, ref, "vit_stage2 bf16"))
+        assert metrics(m.last_scores, ref_scores)["max_rel"] < 2e-2
+
+
+def test_packer(cuda):
+    import hsenet_b200 as H
+    torch.manual_seed(3)
+    p = randomize_params(H.VisualPacker_3d_phi_v3((32, 256, 256), (4, 16, 16), 768, 3072, "mlp", 2)).eval()
+    sd = cpu_state(p)
+    g = torch.Generator().manual_seed(5)
+    tok = torch.randn(2, 2049, 768, generator=g)
+    feats = tok[:, 1:]                                   # the non-contiguous view the tower hands over
+    ref = O.visual_packer(sd, feats)
+    p = p.to(cuda)
+    with torch.no_grad():
+        with H.precision("fp32_verify"):
+            got = p(tok.to(cuda)[:, 1:])
+        assert got.shape == (2, 128, 3072) and p.proj_out_num == 128
+        print("fp32_verify", assert_fp32(got, ref, "packer fp32"))
+        with H.precision("bf16"):
+            got = p(tok.to(cuda)[:, 1:])
+        assert got.dtype == torch.bfloat16
+        print("bf16", assert_bf16(got, ref, "packer bf16"))
+
+
+def test_encode_images_full_path(cuda):
+    """BASELINE config 3 at B=2: dual tower + two packers -> [B,256,3072]."""
+    import hsenet_b200 as H
+    torch.manual_seed(0)
+    enc = randomize_params(H.HSENetVisualEncoder(H.VisionConfig())).eval()
+    tsd = {k: v for k, v in cpu_state(enc.vision_tower).items()}
+    p1, p2 = cpu_state(enc.mm_projector), cpu_state(enc.mm_projector2)
+    x, s = synthetic_inputs(2)
+    ref = O.encode_images(tsd, p1, p2, x, s)
+    enc = enc.to(cuda)
+    with torch.no_grad():
+        with H.precision("fp32_verify"):
+            enc.mm_projector.output_dtype = torch.float32
+            got = enc(x.to(cuda), s.to(cuda))
+        assert got.shape == (2, 256, 3072)
+        print("fp32_verify", assert_fp32(got, ref, "encode_images fp32"))
+        enc.mm_projector.output_dtype = None
+        with H.precision("bf16"):
+            got = enc(x.to(cuda), s.to(cuda))
+        print("bf16", assert_bf16(got, ref, "encode_images bf16"))
+
+
+def test_clip_image_head(cuda):
+    import hsenet_b200 as H
+    torch.manual_seed(2)
+    head = randomize_params(H.ClipImageHead()).eval()
+    sd = cpu_state(head)
+    tok = torch.randn(5, 2049, 768, generator=torch.Generator().manual_seed(1))
+    ref = O.clip_encode_image(sd, tok)
+    head = head.to(cuda)
+    with torch.no_grad():
+        with H.precision("fp32_verify"):
+            got = head(tok.to(cuda))
+        assert_fp32(got, ref, "clip head fp32", tol=1e-5)
+        with H.precision("bf16"):
+            got = head(tok.to(cuda).to(torch.bfloat16))
+        assert_bf16(got, ref, "clip head bf16")
+
+
+def test_no_cpu_path_and_errors(cuda):
+    import hsenet_b200 as H
+    m = _build(H.ViT_stage1, 1)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 32, 256, 256))                 # CPU tensors: must fail loudly, never fall back
+    m = m.to(cuda)
+    with torch.no_grad(), pytest.raises(ValueError):
+        m(torch.zeros(1, 1, 16, 256, 256, device=cuda))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 1, 32, 256, 256, device=cuda))   # grad enabled + trainable params: no silent detach

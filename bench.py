@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- CT volumes/s of the HSENet visual-encoding hot path on B200 (see BASELINE.json / SURVEY.md section 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic volumes per GPU.
+  workload c2 (default, BASELINE.json configs[1]): dual encoder forward -- ViT_stage1 + ViT_stage2 (2E3) on the same
+      batch of 8 volumes per GPU, bf16.  1017.22 algorithmic GFLOP per volume.
+  workload c3 (configs[2]): dual encoder + the two spatial packers -> [B,256,3072], batch 32 per GPU. 1033.54 GFLOP/volume.
+Prints ONE JSON line (rank 0).  `value` = volumes/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = the same through the public module API with pinned HOST inputs, H2D and D2H inside the timed region.
+`--impl reference` times the reference algorithm's CPU path (the oracle port, fp32 eager PyTorch, all host threads) on a
+bounded sample of the same workload; it is the one place outside tests/ and smoke() where oracle/ is executed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_VOLUME = {"c2": 1017.22, "c3": 1033.54}
+DEFAULT_BATCH = {"c2": 8, "c3": 32}
+WORKLOAD_NAME = {
+    "c2": "C2 dual encoder (ViT_stage1 + ViT_stage2/2E3) forward, bf16",
+    "c3": "C3 dual encoder + two spatial packers -> [B,256,3072], bf16",
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1402.0), "bf16_burst": d.get("bf16_tflops", 1673.1),
+                "hbm_gbs": d.get("hbm_gbs", 6555.8), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_modules(workload, device):
+    import hsenet_b200 as H
+    torch.manual_seed(0)
+    enc = H.HSENetVisualEncoder(H.VisionConfig(), use_parallel_projector=True).eval().requires_grad_(False)
+    return enc.to(device)
+
+
+def make_inputs(B, rank, n_sets, pinned):
+    g = torch.Generator().manual_seed(1234 + rank)
+    sets = []
+    for _ in range(n_sets):
+        x = torch.rand(B, 1, 32, 256, 256, generator=g)
+        s = torch.randn(B, 32, 768, generator=g)
+        if pinned:
+            x, s = x.pin_memory(), s.pin_memory()
+        sets.append((x, s))
+    return sets
+
+
+def run_step(enc, workload, x, s):
+    if workload == "c2":
+        return enc.vision_tower(x, s)                 # (feat_stage1 [B,2048,768], feat_stage2 [B,2048,768])
+    return enc(x, s)                                  # [B,256,3072]
+
+
+def cpu_reference_run(workload, threads, reps):
+    """The reference algorithm on host cores: oracle port (fp32 eager PyTorch).  Bounded sample: 1 volume per rep."""
+    from oracle import hsenet_oracle as O
+    import hsenet_b200 as H
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    enc = H.HSENetVisualEncoder(H.VisionConfig(), use_parallel_projector=True).eval()
+    tsd = {k: v.detach().float() for k, v in enc.vision_tower.state_dict().items()}
+    p1 = {k: v.detach().float() for k, v in enc.mm_projector.state_dict().items()}
+    p2 = {k: v.detach().float() for k, v in enc.mm_projector2.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(1, 1, 32, 256, 256, generator=g)
+    s = torch.randn(1, 32, 768, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            if workload == "c2":
+                O.dual_tower(tsd, x, s)
+            else:
+                O.encode_images(tsd, p1, p2, x, s)
+            dt = time.perf_counter() - t0
+            if i > 0:
+                times.append(dt)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--batch", type=int, default=0, help="volumes per GPU per step (default: 8 for c2, 32 for c3)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.batch or DEFAULT_BATCH[args.workload]
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    K = max(args.steps, 1)
+    gflop = GFLOP_PER_VOLUME[args.workload]
+    config = {"workload": WORKLOAD_NAME[args.workload], "volumes_per_gpu_per_step": B, "global_batch": B * world,
+              "volume": "1x32x256x256 fp32 in [0,1]", "tokens": 2049, "hidden": 768, "layers": 12,
+              "parallelism": f"dp{world} (independent volumes per rank, no data-path collective)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        reps = max(1, min(K, 3))
+        times = cpu_reference_run(args.workload, threads, reps)
+        t = statistics.median(times)
+        v = 1.0 / t
+        sample = f"1 volume per step, {len(times)} timed steps after 1 warm-up (median), fp32 eager PyTorch oracle port"
+        print(json.dumps({
+            "impl": "reference", "metric": "CT volumes/s encoded", "value": v, "unit": "volumes/s", "n_gpus": world,
+            "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import hsenet_b200 as H
+    from hsenet_b200 import _lib
+    lib = _lib.load()
+    H.set_precision("bf16")
+    enc = build_modules(args.workload, dev)
+    n_sets = 4                                            # 4 x 67 MB (B=8) of inputs > 126 MB L2: inputs come from HBM
+    host_sets = make_inputs(B, rank, n_sets, pinned=True)
+    dev_sets = [(x.to(dev), s.to(dev)) for x, s in host_sets]
+    config["l2_policy"] = (f"{n_sets} rotating input sets ({n_sets * B * 8.39:.0f} MB) + ~{B * 0.28:.1f} GB of "
+                           "activations per step, both larger than the 126 MB L2; no explicit flush")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for i in range(W):
+            run_step(enc, args.workload, *dev_sets[i % n_sets])
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.hsenet_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            out = run_step(enc, args.workload, *dev_sets[i % n_sets])
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.hsenet_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- roofline pass: the same K steps, instrumented with CUDA events around every launch of the library ----
+        lib.hsenet_profile_start()
+        for i in range(K):
+            run_step(enc, args.workload, *dev_sets[i % n_sets])
+        ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); by = (C.c_double * 4)(); ln = (C.c_uint64 * 4)()
+        _lib.check(lib.hsenet_profile_stop(ms, fl, by, ln), "profile_stop")
+
+        # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region ------------------------------------
+        e2e = None
+        if not args.no_e2e:
+            host_out = []
+
+            def e2e_step(i):
+                x, s = host_sets[i % n_sets]
+                xd = x.to(dev, non_blocking=True)
+                sd = s.to(dev, non_blocking=True)
+                o = run_step(enc, args.workload, xd, sd)
+                outs = o if isinstance(o, tuple) else (o,)
+                if not host_out:
+                    host_out.extend(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs)
+                for h, t in zip(host_out, outs):
+                    h.copy_(t, non_blocking=True)
+                return host_out
+            for i in range(3):
+                e2e_step(i)
+            barrier()
+            e0.record()
+            for i in range(K):
+                res = e2e_step(i)
+            e1.record()
+            barrier()
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+            h2d = host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 4
+            d2h = sum(t.numel() * t.element_size() for t in res)
+            e2e = {"value": B * world * K / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = B * world * K / (ms_total * 1e-3)
+    gemm_tf = fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
+    att_tf = fl[1] / (ms[1] * 1e-3) / 1e12 if ms[1] > 0 else 0.0
+    ln_gbs = by[2] / (ms[2] * 1e-3) / 1e9 if ms[2] > 0 else 0.0
+    step_tf = value / world * gflop / 1e3
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp)).get("gemm_bf16_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "CT volumes/s encoded", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": {
+            "kernel": "gemm_bf16_kernel (tcgen05; 69% of the path's FLOPs)", "bound": "tensor",
+            "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": gemm_tf / peaks["bf16_sustained"], "traffic": traffic,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
+            "launches": int(ln[0]), "avg_launch_ms": ms[0] / ln[0] if ln[0] else None,
+            "how": "algorithmic 2*M*N*K per launch / CUDA-event duration per launch, instrumented re-run of the same steps",
+        },
+        "roofline_attention": {"kernel": "attention_kernel (tcgen05 flash attention; 31% of FLOPs)", "bound": "tensor",
+                               "achieved": att_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                               "frac": att_tf / peaks["bf16_sustained"], "launches": int(ln[1])},
+        "roofline_layernorm": {"kernel": "layernorm_kernel", "bound": "hbm", "achieved": ln_gbs,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ln_gbs / peaks["hbm_gbs"],
+                               "launches": int(ln[2])},
+        "roofline_step": {"achieved": step_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                          "frac": step_tf / peaks["bf16_sustained"], "gflop_per_volume": gflop,
+                          "share_ms": {"gemm": ms[0] / K, "attention": ms[1] / K, "layernorm": ms[2] / K}},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        times = cpu_reference_run(args.workload, threads, 2)
+        t = statistics.median(times)
+        line["cpu_baseline"] = {"value": 1.0 / t, "unit": "volumes/s", "cores": threads, "kind": "port",
+                                "sample": "1 volume per step, 2 timed steps after 1 warm-up (median), fp32 eager "
+                                          "PyTorch oracle port of the reference's vit.py / packer"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,9 @@ SIGNATURES = {
     "hsenet_version": (C.c_char_p, []),
     "hsenet_error_string": (C.c_char_p, [C.c_int]),
     "hsenet_launch_count": (C.c_uint64, []),
+    "hsenet_profile_start": (None, []),
+    "hsenet_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_uint64)]),
     "hsenet_vit_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hsenet_vit_forward": (C.c_int, [C.POINTER(VitWeights), vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                      C.c_size_t, vp]),

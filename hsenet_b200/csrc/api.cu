@@ -2,6 +2,8 @@
 // operator kernels.  No allocation, no synchronisation, no CPU compute: everything is enqueued on the caller's stream.
 #include <atomic>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -10,6 +12,27 @@ namespace hs {
 
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-kernel-class event profiling (bench.py's roofline pass) ------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+static std::atomic<bool> g_prof_on{false};
+
+ProfScope::ProfScope(int cls, double flops, double bytes, cudaStream_t st) : st_(st), idx_(-1) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{nullptr, nullptr, cls, flops, bytes};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  idx_ = static_cast<long>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[idx_].b, st_);
+}
 
 int num_sms() {
   static int n = [] {
@@ -322,6 +345,29 @@ const char* hsenet_error_string(int code) {
 }
 
 uint64_t hsenet_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void hsenet_profile_start(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on.store(true);
+}
+
+int hsenet_profile_stop(double* ms, double* flops, double* bytes, uint64_t* launches) {
+  g_prof_on.store(false);
+  if (cudaDeviceSynchronize() != cudaSuccess) return HSENET_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int c = 0; c < HSENET_PROFILE_CLASSES; ++c) { ms[c] = 0; flops[c] = 0; bytes[c] = 0; launches[c] = 0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < HSENET_PROFILE_CLASSES) {
+      ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return HSENET_OK;
+}
 
 size_t hsenet_vit_workspace_bytes(int B, int precision, int stage) {
   (void)stage;

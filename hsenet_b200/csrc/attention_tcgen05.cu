@@ -256,6 +256,7 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
       return HS_ERR_CUDA;
     attr_set = true;
   }
+  ProfScope prof(PROF_ATTENTION, 4.0 * B * kHeads * double(S) * S * kHeadDim, 2.0 * B * double(S) * 4 * kHidden, stream);
   attention_kernel<<<dim3((S + QT - 1) / QT, kHeads, B), ATT_THREADS, ATT_SMEM, stream>>>(tm, out, S);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;

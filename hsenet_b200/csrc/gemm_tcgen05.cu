@@ -242,6 +242,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   }
   const int tiles = (N / BN) * ((M + BM - 1) / BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 2.0 * (double(M) * K + double(N) * K + double(M) * N), stream);
   gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;

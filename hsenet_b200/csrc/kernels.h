@@ -37,6 +37,15 @@ struct GemmEpilogue {
   int group_offset = 0;
 };
 
+// RAII CUDA-event bracket around one launch, active only between hsenet_profile_start/stop.
+enum : int { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_OTHER = 3 };
+struct ProfScope {
+  ProfScope(int cls, double flops, double bytes, cudaStream_t st);
+  ~ProfScope();
+  cudaStream_t st_;
+  long idx_;
+};
+
 int num_sms();
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer);

@@ -468,6 +468,7 @@ int layernorm_rows(const float* x, long ldx, const float* gamma, const float* be
                    OutT* out2, int seq, cudaStream_t stream) {
   if (rows <= 0) return HS_OK;
   if (!aligned16(x) || (ldx % 4) || (ldo % 4)) return HS_ERR_ALIGN;
+  ProfScope prof(PROF_LAYERNORM, 0.0, double(rows) * kHidden * (4.0 + sizeof(OutT) * ((out != nullptr) + (out2 != nullptr))), stream);
   layernorm_kernel<OutT><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, gamma, beta, rows, out,
                                                                                     ldo, out2, seq);
   count_launch();

@@ -110,6 +110,13 @@ const char* hsenet_error_string(int code);
 /* Number of kernels launched by this library in this process so far (bench.py's `gpu_launches`). */
 uint64_t hsenet_launch_count(void);
 
+/* Per-kernel-class CUDA-event timing (used by bench.py's roofline pass; off by default, zero cost when off).
+ * Classes: 0 = tcgen05 GEMM, 1 = self attention, 2 = LayerNorm, 3 = everything else.  stop() synchronises the device
+ * and fills, per class: summed milliseconds, algorithmic FLOPs, algorithmic bytes, launch count (arrays of 4). */
+#define HSENET_PROFILE_CLASSES 4
+void hsenet_profile_start(void);
+int hsenet_profile_stop(double* ms, double* flops, double* bytes, uint64_t* launches);
+
 /* ---- composite entry points ----------------------------------------------------------------------------------- */
 
 /* Replaces ViT_stage1.forward (vit.py:449-469) / ViT_stage2.forward (vit.py:315-357).

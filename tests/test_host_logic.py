@@ -1,0 +1,126 @@
+"""Host-side logic on CPU: facade contracts, error behaviour, weight cache, world_size-2 gloo gather_features."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from util import GEOM
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_constructor_contract_and_errors():
+    import hsenet_b200 as H
+    with pytest.raises(ValueError):
+        H.ViT_stage1(1, (32, 256, 256), (4, 16, 16), hidden_size=770, num_heads=12, pos_embed="perceptron",
+                     classification=True)
+    with pytest.raises(ValueError):
+        H.ViT_stage1(1, (64, 256, 256), (4, 16, 16), pos_embed="perceptron", classification=True)
+    with pytest.raises(ValueError):
+        H.ViT_stage1(dropout_rate=1.5, **GEOM)
+    cfg = H.VisionConfig()
+    cfg.vision_tower = "something_else"
+    with pytest.raises(ValueError, match="Unknown vision tower"):
+        H.build_vision_tower(cfg)
+    cfg = H.VisionConfig()
+    cfg.mm_projector_type = "nope"
+    with pytest.raises(ValueError, match="Unknown projector type"):
+        H.build_mm_projector(cfg)
+    cfg = H.VisionConfig(select_feature="bogus")
+    t = H.build_vision_tower(cfg)
+    with pytest.raises(ValueError, match="Unexpected select feature"):
+        t(torch.zeros(1, 1, 32, 256, 256), torch.zeros(1, 32, 768))
+
+
+def test_cpu_inputs_fail_loudly_no_fallback():
+    import hsenet_b200 as H
+    m = H.ViT_stage1(num_layers=1, **GEOM).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 1, 32, 256, 256))
+    p = H.VisualPacker_3d_phi_v3((32, 256, 256), (4, 16, 16), 768, 3072, "mlp", 2).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        p(torch.zeros(1, 2048, 768))
+
+
+def test_state_dict_roundtrip_and_deepcopy():
+    import hsenet_b200 as H
+    a = H.ViT_stage2(num_layers=2, **GEOM)
+    b = H.ViT_stage2(num_layers=2, **GEOM)
+    b.load_state_dict(a.state_dict(), strict=True)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    c = copy.deepcopy(a)
+    assert list(c.state_dict().keys()) == list(a.state_dict().keys())
+    assert a.patch_embedding.patch_embeddings[1].weight.shape == (768, 1024)
+    assert a.blocks[0].attn.qkv.bias is None and a.blocks[0].attn.qkv.weight.shape == (2304, 768)
+
+
+def test_weight_cache_invalidation():
+    from hsenet_b200 import runtime as rt
+    lin = torch.nn.Linear(4, 4)
+    cache, calls = rt.WeightCache(), []
+    build = lambda p: calls.append(p) or len(calls)
+    assert cache.get(lin.parameters(), "bf16", build) == 1
+    assert cache.get(lin.parameters(), "bf16", build) == 1            # unchanged -> cached
+    with torch.no_grad():
+        lin.weight.add_(1.0)                                          # optimizer-style in-place update
+    assert cache.get(lin.parameters(), "bf16", build) == 2
+    assert cache.get(lin.parameters(), "fp32_verify", build) == 3     # precision switch
+    lin.load_state_dict({k: v.clone() for k, v in lin.state_dict().items()})
+    assert cache.get(lin.parameters(), "fp32_verify", build) == 4
+
+
+def test_precision_context():
+    import hsenet_b200 as H
+    assert H.get_precision() in ("bf16", "fp32_verify")
+    with H.precision("fp32_verify"):
+        assert H.get_precision() == "fp32_verify"
+        with H.precision("bf16"):
+            assert H.get_precision() == "bf16"
+        assert H.get_precision() == "fp32_verify"
+    with pytest.raises(ValueError):
+        H.set_precision("fp8")
+
+
+# ---- world_size 2 over gloo: packed single all-gather == the reference's two all-gathers, incl. gradients ----------
+def _gather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import torch.distributed.nn
+    from hsenet_b200 import gather_features
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        img = torch.randn(3, 768, generator=g, requires_grad=True)
+        txt = torch.randn(3, 768, generator=g, requires_grad=True)
+        ai, at = gather_features(img, txt, rank=rank, world_size=world)
+        # the reference's formulation (utils/dist_utils.py:292-293)
+        ri = torch.cat(torch.distributed.nn.all_gather(img), dim=0)
+        rt_ = torch.cat(torch.distributed.nn.all_gather(txt), dim=0)
+        ok = torch.equal(ai, ri) and torch.equal(at, rt_) and ai.shape == (3 * world, 768)
+        w = torch.arange(1, 3 * world + 1, dtype=torch.float32).unsqueeze(1)
+        (gi, gt) = torch.autograd.grad(((ai * w).sum() + 2 * (at * w).sum()), (img, txt))
+        (hi, ht) = torch.autograd.grad(((ri * w).sum() + 2 * (rt_ * w).sum()), (img, txt))
+        ok = ok and torch.allclose(gi, hi) and torch.allclose(gt, ht)
+        # no-grad variant keeps the local block differentiable (dist_utils.py:300-303)
+        bi, bt = gather_features(img, txt, gather_with_grad=False, rank=rank, world_size=world)
+        ok = ok and torch.equal(bi.detach(), ri.detach()) and bi.requires_grad
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_features_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

@@ -15,6 +15,7 @@
 //     and an output row remap (used to write patch tokens behind the cls row and packer tokens into their
 //     [B,256,3072] slot, replacing the reference's torch.cat calls).
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 
 namespace hs {
@@ -31,8 +32,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;            // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_PITCH = 33;
-constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;   // 33,792 B
+constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;       // 32 KB
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;            // 320
 constexpr int TMEM_COLS = 512;                              // 2 accumulator stages x 256 fp32 columns
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -45,6 +45,7 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmEpilogue ep, int M, int N, int K) {
@@ -52,7 +53,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* smem_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t smem_epi = smem_u32(smem + STAGES * STAGE_BYTES);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -135,9 +136,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 2;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int col_half = ew >> 2;            // which 128-column half of the tile
-    float* stage = smem_epi + ew * 32 * EPI_PITCH;
-    const int sub_row = lane >> 3;           // 0..3   (readback: 4 rows per pass)
-    const int sub_col = (lane & 7) * 4;      // 0..28  (4 consecutive columns per lane)
+    const uint32_t stage = smem_epi + ew * EPI_WARP_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -145,63 +144,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (tile % n_tiles) * BN;
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int c0 = col_half * 128 + chunk * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, v);
-        tmem_ld_wait();
-        if (chunk == 3) {
-          // all TMEM reads of this accumulator stage by this warp are done: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const int col = n0 + c0 + sub_col;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + sub_row;
-          const int row = m0 + quarter * 32 + r;
-          if (row < M) {
-            float4 x;
-            x.x = stage[r * EPI_PITCH + sub_col + 0] + bias4.x;
-            x.y = stage[r * EPI_PITCH + sub_col + 1] + bias4.y;
-            x.z = stage[r * EPI_PITCH + sub_col + 2] + bias4.z;
-            x.w = stage[r * EPI_PITCH + sub_col + 3] + bias4.w;
-            long orow = row;
-            if (ep.rows_per_group > 0) {
-              const int g = row / ep.rows_per_group;
-              const int rr = row - g * ep.rows_per_group;
-              orow = static_cast<long>(g) * ep.group_stride + ep.group_offset + rr;
-              if (ep.row_add != nullptr) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(ep.row_add + static_cast<long>(rr) * N + col));
-                x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
-              }
-            }
-            if (ep.resid != nullptr) {
-              const float4 a = *reinterpret_cast<const float4*>(ep.resid + orow * ep.ld_resid + col);
-              x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
-            }
-            if (ep.gelu) {
-              x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
-            }
-            if (ep.out_f32 != nullptr) *reinterpret_cast<float4*>(ep.out_f32 + orow * ep.ld_f32 + col) = x;
-            if (ep.out_bf16 != nullptr) {
-              uint2 pk;
-              pk.x = pack_bf16x2(x.x, x.y);
-              pk.y = pack_bf16x2(x.z, x.w);
-              *reinterpret_cast<uint2*>(ep.out_bf16 + orow * ep.ld_bf16 + col) = pk;
-            }
-          }
-        }
-        __syncwarp();
-      }
+      uint64_t* empty_bar = &bars->tmem_empty[acc];
+      epilogue_slab<MODE>(ep, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_half * 128, stage,
+                    m0 + quarter * 32, n0 + col_half * 128, M, N, lane, [&]() {
+                      // all TMEM reads of this accumulator stage by this warp are done: hand it back to the MMA warp
+                      tc_fence_before();
+                      __syncwarp();
+                      if (lane == 0) mbar_arrive(empty_bar);
+                    });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -219,8 +169,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
-              cudaStream_t stream) {
+int gemm_bf16_1cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                   cudaStream_t stream) {
   if (M <= 0) return HS_OK;
   if (N % BN != 0 || K % BK != 0) return HS_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (lda % 8) || (ldw % 8))
@@ -235,15 +185,23 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   if (rc != HS_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
-        cudaSuccess)
-      return HS_ERR_CUDA;
+    bool ok = true;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_F32_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    if (!ok) return HS_ERR_CUDA;
     attr_set = true;
   }
   const int tiles = (N / BN) * ((M + BM - 1) / BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 2.0 * (double(M) * K + double(N) * K + double(M) * N), stream);
-  gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K);
+  switch (epilogue_mode(ep)) {
+    case EPI_BF16: gemm_bf16_kernel<EPI_BF16><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16_GELU: gemm_bf16_kernel<EPI_BF16_GELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
+    case EPI_F32_RESID: gemm_bf16_kernel<EPI_F32_RESID><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
+    default: gemm_bf16_kernel<EPI_GENERIC><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
+  }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
 }

@@ -71,12 +71,20 @@ def _gemm(lib, A, W, bias=None, resid=None, gelu=False, prec=0, want_f32=True, w
     return of, oa
 
 
+@pytest.fixture(params=["2cta", "1cta"])
+def gemm_variant(request, monkeypatch):
+    """The dispatcher reads HSENET_GEMM_1CTA per call: exercise the CTA-pair kernel and the 1-CTA kernel."""
+    monkeypatch.setenv("HSENET_GEMM_1CTA", "1" if request.param == "1cta" else "0")
+    return request.param
+
+
 GEMM_SHAPES = [(128, 256, 64), (300, 256, 128), (2049, 768, 768), (4098, 2304, 768), (1000, 768, 3072),
-               (64, 1536, 768), (2, 768, 768), (4096, 768, 1024)]
+               (64, 1536, 768), (2, 768, 768), (4096, 768, 1024), (16392, 768, 768), (257, 512, 64),
+               (20000, 256, 3072)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_bf16_plain(lib, cuda, M, N, K):
+def test_gemm_bf16_plain(lib, cuda, gemm_variant, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g).to(torch.bfloat16)
     W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
@@ -88,7 +96,7 @@ def test_gemm_bf16_plain(lib, cuda, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(2049, 768, 768), (513, 3072, 768)])
-def test_gemm_bf16_epilogues(lib, cuda, M, N, K):
+def test_gemm_bf16_epilogues(lib, cuda, gemm_variant, M, N, K):
     g = torch.Generator().manual_seed(11)
     A = torch.randn(M, K, generator=g).to(torch.bfloat16)
     W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
@@ -105,7 +113,7 @@ def test_gemm_bf16_epilogues(lib, cuda, M, N, K):
     assert metrics(of, base + resid)["max_rel"] < 2e-5
 
 
-def test_gemm_bf16_inplace_residual(lib, cuda):
+def test_gemm_bf16_inplace_residual(lib, cuda, gemm_variant):
     from hsenet_b200 import _lib
     M, N, K = 1500, 768, 768
     g = torch.Generator().manual_seed(5)

@@ -1,21 +1,28 @@
 // Fused flash-style self attention for the 3D token sequence (MONAI SABlock core as used by vit.py:438-443):
 //     out[b, :, h*64:(h+1)*64] = softmax(Q_h K_h^T / sqrt(64)) V_h,   S = 2049 tokens, 12 heads x 64.
 // The reference materialises the [B,12,2049,2049] score tensor (201 MB/layer/volume in fp32); here scores never
-// leave the SM: S = Q K^T accumulates in TMEM, the softmax warps turn it into bf16 P (also in TMEM), and
-// O += P V runs with P as the TMEM-resident A operand.
+// leave the SM: S = Q K^T accumulates in TMEM, the softmax warps turn it into bf16 P (also TMEM), and O += P V runs
+// with P as the TMEM-resident A operand.
 //
 // CTA = one 128-query tile of one (batch, head); 2 CTAs are co-resident per SM (256 TMEM columns each).
-// Keys are processed in 64-key sub-tiles with DOUBLE-BUFFERED score / probability tiles in TMEM:
-//     columns   0.. 63  S0      64..127  S1     128..159  P0     160..191  P1     192..255  O
-// so Q K^T of sub-tile t+1 (and t+2) is already in flight while the softmax warps work on sub-tile t, and the
-// softmax is single pass (64 fp32 scores per thread live in registers).
-//   warp 0      TMA producer: Q once, then K / V 128-key tiles straight out of the fused qkv activation
-//               [B*S, 2304] (column offsets 0 / 768 / 1536 + h*64) -- no head-split copies are ever made;
-//   warp 1      single-thread tcgen05.mma issuer: S = Q K^T (SS, both K-major, N = 64),
-//               O += P V (TS: P from TMEM, V is the MN-major B operand straight from its row-major tile);
-//   warps 2..5  online softmax in fp32 (exp2 domain, lazy rescale), O correction, final normalise + bf16 store.
-// Keys past the end of the sequence (2049 = 32*64 + 1) are masked in the last sub-tile; softmax warps whose 32 query
-// rows are all past the end (last query tile) skip the exponentials.
+// Keys are processed in 64-key steps with DOUBLE-BUFFERED score and probability tiles:
+//     TMEM columns   0.. 63  S0      64..127  S1     128..159  P0     160..191  P1     192..255  O
+//   warp 0 lane 0  TMA producer: Q once, then K / V 128-key tiles straight out of the fused qkv activation
+//                  [B*S, 2304] (column offsets 0 / 768 / 1536 + h*64) -- no head-split copies are ever made;
+//   warp 1 lane 0  Q K^T issuer: S[b] = Q K^T (SS, both K-major, N = 64) for step t as soon as step t-2 has pulled its
+//                  scores into registers (s_free) and P V (t-2) has retired (pv_done) -- two steps ahead of the softmax;
+//   warp 0 lane 1  P V issuer: O += P[b] V (TS: P from TMEM, V is the MN-major B operand straight from its row-major
+//                  tile) as soon as P[b] is stored (p_full);
+//   warps 2..5     single-pass online softmax in fp32 (exp2 domain, lazy rescale): ONE mbarrier wait per step
+//                  (s_full, which also certifies that P[b] is free), 64 scores per thread in registers; O correction
+//                  only when the running max moved by more than 2^8; final normalise + bf16 store.
+// Why this shape (measured on B200: tools/umma_latency.cu, tools/ldtm_bw.cu, profiles/README.md): an mbarrier hop
+// costs ~250-300 cycles even when the phase is already complete and each tcgen05.mma issue 50-100 cycles on a busy SM,
+// while the exponentials of a 128x64 step need only 512 MUFU cycles per warp.  Earlier versions (single score buffer
+// and/or one issuing thread) serialised softmax and MMA chain and plateaued at ~195 us per layer for 8 volumes; here
+// both chains run two steps ahead of the softmax warps, which never wait on the tensor pipe.
+// Keys past the end of the sequence (2049 = 32*64 + 1) are masked in the last step; softmax warps whose 32 query rows
+// are all past the end (last query tile) skip the exponentials.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -27,7 +34,7 @@ namespace {
 
 constexpr int QT = 128;                    // queries per CTA
 constexpr int KT = 128;                    // keys per TMA tile
-constexpr int KS = 64;                     // keys per softmax / MMA sub-tile
+constexpr int KS = 64;                     // keys per softmax / MMA step
 constexpr int K_STAGES = 3;
 constexpr int V_STAGES = 2;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
@@ -41,7 +48,7 @@ struct AttBarriers {
   uint64_t q_full;
   uint64_t k_full[K_STAGES], k_empty[K_STAGES];
   uint64_t v_full[V_STAGES], v_empty[V_STAGES];
-  uint64_t s_full[2], p_full[2], pv_done[2];
+  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
   uint32_t tmem_base;
 };
 
@@ -67,7 +74,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   const int b = blockIdx.z;
   const int row0 = b * S;                      // first row of this volume in the [B*S, 2304] activation
   const int ntiles = (S + KT - 1) / KT;        // 128-key TMA tiles
-  const int nsub = (S + KS - 1) / KS;          // 64-key sub-tiles
+  const int nsub = (S + KS - 1) / KS;          // 64-key steps
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -76,6 +83,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     for (int s = 0; s < V_STAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_free[i], 4);
       mbar_init(&bars->p_full[i], 4);
       mbar_init(&bars->pv_done[i], 1);
     }
@@ -91,8 +99,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
     if (lane == 0) {
+      // ===================== TMA producer =====================
       mbar_arrive_expect_tx(&bars->q_full, TILE_BYTES);
       tma_load_2d(sQ, &tmQKV, &bars->q_full, h * kHeadDim, row0 + q0);
       for (int j = 0; j < ntiles; ++j) {
@@ -106,41 +114,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         tma_load_2d_hint(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * kHidden + h * kHeadDim,
                          row0 + j * KT, kEvictLast);
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
+    } else if (lane == 1) {
+      // ===================== P V issuer =====================
       constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);    // O[128q x 64d] += P V (V MN-major)
-      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
-      auto issue_qk = [&](int t) {
-        const int j = t >> 1, ks = j % K_STAGES;
-        if ((t & 1) == 0) {                         // first sub-tile of a new K tile: wait for its TMA
-          mbar_wait(&bars->k_full[ks], (j / K_STAGES) & 1);
-          tc_fence_after();
-        }
-        const uint64_t kdesc =
-            make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + (t & 1) * SUB_BYTES));
-#pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ss(tmem_base + COL_S + (t & 1) * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        if ((t & 1) == 1 || t == nsub - 1) tc_commit(&bars->k_empty[ks]);   // K tile fully consumed
-        tc_commit(&bars->s_full[t & 1]);
-      };
-      mbar_wait(&bars->q_full, 0);
-      tc_fence_after();
-      issue_qk(0);
-      if (nsub > 1) issue_qk(1);
       for (int t = 0; t < nsub; ++t) {
-        const int bsel = t & 1;
-        mbar_wait(&bars->p_full[bsel], (t >> 1) & 1);   // softmax t done: S[bsel] consumed, P[bsel] written
+        const int bsel = t & 1, j = t >> 1, vs = j % V_STAGES;
+        if (bsel == 0) mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+        mbar_wait(&bars->p_full[bsel], (t >> 1) & 1);       // softmax t done: P[bsel] stored, O rescaled if needed
         tc_fence_after();
-        if (t + 2 < nsub) issue_qk(t + 2);              // refill the score buffer first
-        const int j = t >> 1, vs = j % V_STAGES;
-        if (bsel == 0) {
-          mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
-          tc_fence_after();
-        }
         const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + bsel * SUB_BYTES));
 #pragma unroll
         for (int k = 0; k < KS / 16; ++k) {
@@ -148,8 +129,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           umma_ts(tmem_base + COL_O, tmem_base + COL_P + bsel * 32 + 8 * k, vdesc + 128 * k, idesc_pv,
                   (t | k) != 0 ? 1u : 0u);
         }
-        if (bsel == 1 || t == nsub - 1) tc_commit(&bars->v_empty[vs]);      // V tile fully consumed
         tc_commit(&bars->pv_done[bsel]);
+        if (bsel == 1 || t == nsub - 1) tc_commit(&bars->v_empty[vs]);      // V tile fully consumed
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== Q K^T issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
+      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
+      mbar_wait(&bars->q_full, 0);
+      for (int t = 0; t < nsub; ++t) {
+        const int bsel = t & 1, j = t >> 1, ks = j % K_STAGES;
+        if (bsel == 0) mbar_wait(&bars->k_full[ks], (j / K_STAGES) & 1);
+        if (t >= 2) {
+          const uint32_t par = ((t >> 1) - 1) & 1;
+          mbar_wait(&bars->s_free[bsel], par);     // step t-2 holds its scores in registers: S[bsel] may be overwritten
+          mbar_wait(&bars->pv_done[bsel], par);    // P V (t-2) retired: P[bsel] may be overwritten by step t
+        }
+        tc_fence_after();
+        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + bsel * SUB_BYTES));
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss(tmem_base + COL_S + bsel * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        tc_commit(&bars->s_full[bsel]);
+        if (bsel == 1 || t == nsub - 1) tc_commit(&bars->k_empty[ks]);      // K tile fully consumed
       }
     }
   } else {
@@ -163,43 +167,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     float l = 0.f;
     for (int t = 0; t < nsub; ++t) {
       const int bsel = t & 1;
-      mbar_wait(&bars->s_full[bsel], (t >> 1) & 1);
+      mbar_wait(&bars->s_full[bsel], (t >> 1) & 1);      // S[bsel] ready and P[bsel] free
       tc_fence_after();
-      uint32_t p[32];
+      uint32_t x[64];
+      uint32_t pk[32];
       float alpha = 1.f;
       if (warp_live) {
-        uint32_t x[64];
         tmem_ld32(tmem_base + lane_base + COL_S + bsel * KS, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
         tmem_ld32(tmem_base + lane_base + COL_S + bsel * KS + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
         tmem_ld_wait();
+      }
+      // the scores are in registers: the Q K^T issuer may refill S[bsel] (for step t+2) while we exponentiate
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_free[bsel]);
+      if (warp_live) {
         const int kbase = t * KS;
-        if (kbase + KS > S) {                            // last sub-tile: mask keys past the sequence end
+        if (kbase + KS > S) {                            // last step: mask keys past the sequence end
 #pragma unroll
           for (int i = 0; i < 64; ++i)
             if (kbase + i >= S) x[i] = 0xff800000u;      // -inf
         }
-        float tmax = __uint_as_float(x[0]);
+        float mx[4];
 #pragma unroll
-        for (int i = 1; i < 64; ++i) tmax = fmaxf(tmax, __uint_as_float(x[i]));
+        for (int u = 0; u < 4; ++u) mx[u] = __uint_as_float(x[u]);
+#pragma unroll
+        for (int i = 4; i < 64; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(x[i + u]));
+        }
+        const float tm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
         // running max with lazy rescale: only move the reference max when it grows by more than 2^8
-        const float tm = tmax * c;
         if (tm > m + 8.0f) {
-          alpha = ex2(m - tm);                           // m = -inf on the first sub-tile -> 0
+          alpha = ex2(m - tm);                           // m = -inf on the first step -> 0
           m = tm;
         }
-        float rsum = 0.f;
+        float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
-          const float e0 = ex2(fmaf(__uint_as_float(x[i]), c, -m));
+          const float e0 = ex2(fmaf(__uint_as_float(x[i + 0]), c, -m));
           const float e1 = ex2(fmaf(__uint_as_float(x[i + 1]), c, -m));
-          rsum += e0 + e1;
-          p[i >> 1] = pack_bf16x2(e0, e1);
+          rs0 += e0;
+          rs1 += e1;
+          pk[i >> 1] = pack_bf16x2(e0, e1);
         }
-        l = l * alpha + rsum;
+        l = l * alpha + (rs0 + rs1);
+        tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, pk);
       }
-      // O correction (rare): needs P V (t-1) retired
+      // O correction (rare after the first steps): P V (t-1) must have retired before O is rescaled
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(&bars->pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
+        mbar_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll 1
@@ -211,12 +228,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           tmem_st32(tmem_base + lane_base + COL_O + ch * 32, o);
         }
       }
-      // P[bsel] was last read by P V (t-2): it must have retired before we overwrite it
-      if (t >= 2) {
-        mbar_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
-        tc_fence_after();
-      }
-      tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, p);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -227,20 +238,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     mbar_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
-    uint32_t x[32];
+    uint32_t o[32];
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
-      tmem_ld32(tmem_base + lane_base + COL_O + ch * 32, x);
+      tmem_ld32(tmem_base + lane_base + COL_O + ch * 32, o);
       tmem_ld_wait();
       if (qi < S) {
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long>(row0) + qi) * kHidden + h * kHeadDim + ch * 32);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(x[g * 8 + 0]) * inv, __uint_as_float(x[g * 8 + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(x[g * 8 + 2]) * inv, __uint_as_float(x[g * 8 + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(x[g * 8 + 4]) * inv, __uint_as_float(x[g * 8 + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(x[g * 8 + 6]) * inv, __uint_as_float(x[g * 8 + 7]) * inv);
+          u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
           dst[g] = u;
         }
       }

@@ -231,54 +231,92 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        launches0 = lib.hsenet_launch_count()
+        from hsenet_b200 import runtime as hrt
+        launches0 = hrt.kernel_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_host0 = time.perf_counter()
         e0.record()
         for i in range(K):
             out = run_step(enc, args.workload, *dev_sets[i % n_sets])
         e1.record()
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
-        launches = lib.hsenet_launch_count() - launches0
+        launches = hrt.kernel_launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- roofline pass: the same K steps, instrumented with CUDA events around every launch of the library ----
+        # (direct launches: the per-launch event hooks live in the library's launchers, which graph replays bypass)
+        for tw in (enc.vision_tower.vision_tower_stage1, enc.vision_tower.vision_tower_stage2):
+            tw.use_cuda_graph = False
         lib.hsenet_profile_start()
         for i in range(K):
             run_step(enc, args.workload, *dev_sets[i % n_sets])
         ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); by = (C.c_double * 4)(); ln = (C.c_uint64 * 4)()
         _lib.check(lib.hsenet_profile_stop(ms, fl, by, ln), "profile_stop")
+        for tw in (enc.vision_tower.vision_tower_stage1, enc.vision_tower.vision_tower_stage2):
+            tw.use_cuda_graph = True
 
         # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region ------------------------------------
         e2e = None
         if not args.no_e2e:
-            host_out = []
+            # Double-buffered ingest loop: H2D of step i+1 and D2H of step i-1 run on side streams while step i
+            # computes.  Every step still moves its own inputs host->device and its own result device->host inside
+            # the timed region; they are overlapped, not skipped.
+            cur = torch.cuda.current_stream(dev)
+            s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            xd = [torch.empty_like(dev_sets[0][0]) for _ in range(2)]
+            sd = [torch.empty_like(dev_sets[0][1]) for _ in range(2)]
+            ev_in = [torch.cuda.Event() for _ in range(2)]
+            ev_done = [torch.cuda.Event() for _ in range(2)]
+            ev_out = [torch.cuda.Event() for _ in range(2)]
+            host_out = [None, None]
+            used = [False, False]
 
             def e2e_step(i):
+                slot = i & 1
                 x, s = host_sets[i % n_sets]
-                xd = x.to(dev, non_blocking=True)
-                sd = s.to(dev, non_blocking=True)
-                o = run_step(enc, args.workload, xd, sd)
+                with torch.cuda.stream(s_h2d):
+                    if used[slot]:
+                        s_h2d.wait_event(ev_done[slot])          # step i-2 has finished reading this input slot
+                    xd[slot].copy_(x, non_blocking=True)
+                    sd[slot].copy_(s, non_blocking=True)
+                    ev_in[slot].record(s_h2d)
+                cur.wait_event(ev_in[slot])
+                o = run_step(enc, args.workload, xd[slot], sd[slot])
+                ev_done[slot].record(cur)
                 outs = o if isinstance(o, tuple) else (o,)
-                if not host_out:
-                    host_out.extend(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs)
-                for h, t in zip(host_out, outs):
-                    h.copy_(t, non_blocking=True)
-                return host_out
-            for i in range(3):
+                if host_out[slot] is None:
+                    host_out[slot] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev_done[slot])
+                    if used[slot]:
+                        pass                                      # host buffers are reused in order on one stream
+                    for hbuf, t in zip(host_out[slot], outs):
+                        t.record_stream(s_d2h)
+                        hbuf.copy_(t, non_blocking=True)
+                    ev_out[slot].record(s_d2h)
+                used[slot] = True
+                return host_out[slot]
+
+            for i in range(4):
                 e2e_step(i)
             barrier()
+            s_d2h.synchronize()
             e0.record()
             for i in range(K):
                 res = e2e_step(i)
+            cur.wait_stream(s_d2h)                               # the last results must be on the host before we stop
             e1.record()
             barrier()
             ms_e2e = max_over_ranks(e0.elapsed_time(e1))
             h2d = host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 4
             d2h = sum(t.numel() * t.element_size() for t in res)
             e2e = {"value": B * world * K / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K}
+                   "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                   "how": "public module API, pinned host inputs/outputs, H2D and D2H of every step inside the timed "
+                          "region on side streams (double buffered) overlapping the previous/next step's compute"}
 
     if rank != 0:
         if world > 1:
@@ -302,6 +340,7 @@ def main():
         "metric": "CT volumes/s encoded", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": {
             "kernel": "gemm_bf16_kernel (tcgen05; 69% of the path's FLOPs)", "bound": "tensor",
             "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",

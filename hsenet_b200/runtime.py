@@ -156,5 +156,54 @@ class WeightCache:
         return self.payload
 
 
+_graph_kernels = 0
+
+
+def note_graph_kernels(n: int) -> None:
+    """Kernels launched on the device through CUDA-graph replays (the library's own counter only sees direct calls)."""
+    global _graph_kernels
+    _graph_kernels += n
+
+
+def kernel_launch_count() -> int:
+    """Total hsenet_b200 kernels launched by this process: direct launches + kernels inside replayed graphs."""
+    return int(_lib.load().hsenet_launch_count()) + _graph_kernels
+
+
+class GraphCache:
+    """Captured CUDA graphs of a module's forward, keyed by the call shape; an entry is only valid for the weight-cache
+    payload and workspace address it was captured with (both are baked into the graph as raw pointers)."""
+
+    def __init__(self, max_entries: int = 8):
+        self.entries = {}
+        self.max_entries = max_entries
+
+    def __deepcopy__(self, memo):
+        return GraphCache(self.max_entries)
+
+    def __getstate__(self):
+        return {"max_entries": self.max_entries}
+
+    def __setstate__(self, state):
+        self.__init__(state.get("max_entries", 8))
+
+    def get(self, key, payload_id, ws_ptr):
+        ent = self.entries.get(key)
+        if ent is None or ent["_payload_id"] != payload_id or ent["_ws_ptr"] != ws_ptr:
+            return None
+        return ent
+
+    def put(self, key, payload_id, ws_ptr, ent):
+        if len(self.entries) >= self.max_entries and key not in self.entries:
+            self.entries.pop(next(iter(self.entries)))
+        ent["_payload_id"] = payload_id
+        ent["_ws_ptr"] = ws_ptr
+        self.entries[key] = ent
+        return ent
+
+    def clear(self):
+        self.entries.clear()
+
+
 def ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()

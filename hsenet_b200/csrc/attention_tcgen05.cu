@@ -58,19 +58,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^y on the FMA/ALU pipes (no MUFU): round-to-nearest split y = n + f, f in [-0.5, 0.5], cubic for 2^f (relative
-// error < 7e-4, well inside bf16's 2^-9), exponent patched in with integer adds.  Used for a fraction of the
-// exponentials to take load off the MUFU pipe, which bounds the softmax (16 ex2/clk/SM vs 8192 MMA flop/clk/SM).
-__device__ __forceinline__ float exp2_poly(float y) {
-  y = fmaxf(y, -126.0f);
-  const float t = y + 12582912.0f;                       // 1.5 * 2^23: integer part lands in the low mantissa bits
-  const float f = y - (t - 12582912.0f);
-  float p = fmaf(f, 0.0555041f, 0.2402265f);
-  p = fmaf(p, f, 0.6931472f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S) {
   extern __shared__ uint8_t smem_raw[];
@@ -217,15 +204,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         }
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
+        for (int i = 0; i < 64; i += 2) {
           const float e0 = ex2(fmaf(__uint_as_float(x[i + 0]), c, -m));
           const float e1 = ex2(fmaf(__uint_as_float(x[i + 1]), c, -m));
-          const float e2 = ex2(fmaf(__uint_as_float(x[i + 2]), c, -m));
-          const float e3 = exp2_poly(fmaf(__uint_as_float(x[i + 3]), c, -m));   // 1 in 4 on the FMA pipe
-          rs0 += e0 + e2;
-          rs1 += e1 + e3;
-          pk[(i >> 1) + 0] = pack_bf16x2(e0, e1);
-          pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+          rs0 += e0;
+          rs1 += e1;
+          pk[i >> 1] = pack_bf16x2(e0, e1);
         }
         l = l * alpha + (rs0 + rs1);
         tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, pk);

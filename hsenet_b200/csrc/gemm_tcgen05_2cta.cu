@@ -4,7 +4,7 @@
 // measured ~10 TB/s aggregate on B200 = ~45 % of the tensor peak).  A CTA pair computes a 256x256 tile with
 // UMMA 256x256x16: each CTA stages only its own 128 rows of A and HALF of the B tile (32 KB per k-block), the tensor
 // cores of both SMs read the peer's half of B through the pair's shared window.  Operand traffic per FLOP drops by a
-// third and the smem ring gets 6 stages.
+// third.  The smem ring has 3 stages of K = 128 (64 KB per CTA per stage).
 //
 //   cluster (2,1,1); persistent: one pair per SM pair, static tile order (N fastest)
 //   warp 0   TMA producer of THIS CTA's operand halves (cp.async.bulk.tensor ... .cta_group::2, signalling the
@@ -30,10 +30,11 @@ namespace {
 
 constexpr int PM = 256;                     // pair tile rows   (128 per CTA)
 constexpr int PN = 256;                     // pair tile cols   (each CTA stages 128 of the 256 W rows)
-constexpr int BK = 64;
-constexpr int STAGES = 6;
-constexpr int A_STAGE_BYTES = 128 * BK * 2; // 16 KB
-constexpr int B_STAGE_BYTES = 128 * BK * 2; // 16 KB
+constexpr int BK = 128;                     // K per pipeline stage = two 64-column (128-byte swizzle) TMA boxes per operand
+constexpr int STAGES = 3;
+constexpr int SUB_BYTES = 128 * 64 * 2;     // one [128 rows x 64 cols] swizzled sub-tile, 16 KB
+constexpr int A_STAGE_BYTES = 2 * SUB_BYTES; // 32 KB
+constexpr int B_STAGE_BYTES = 2 * SUB_BYTES; // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
@@ -155,6 +156,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
           tma_load_2d_2cta(smem_a + s * A_STAGE_BYTES, &tmA, &bars->full[s], kb * BK, m0, kEvictNormal);
           tma_load_2d_2cta(smem_b + s * B_STAGE_BYTES, &tmB, &bars->full[s], kb * BK, n0, kEvictLast);
+          tma_load_2d_2cta(smem_a + s * A_STAGE_BYTES + SUB_BYTES, &tmA, &bars->full[s], kb * BK + 64, m0,
+                           kEvictNormal);
+          tma_load_2d_2cta(smem_b + s * B_STAGE_BYTES + SUB_BYTES, &tmB, &bars->full[s], kb * BK + 64, n0,
+                           kEvictLast);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
@@ -176,9 +181,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
+          // 8 MMAs per barrier round trip (an mbarrier wait costs ~250 cycles, as much as two of these MMAs):
+          // k = 0..3 walk the first swizzled sub-tile (+32 B each), k = 4..7 the second (+16 KB = 1024 x 16 B)
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t off = (k >> 2) * (SUB_BYTES >> 4) + 2 * (k & 3);
+            umma_ss_2cta(tmem_d, adesc + off, bdesc + off, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           tc_commit_2cta(&bars->empty[s]);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
@@ -230,9 +239,9 @@ int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N,
   if (ep.out_bf16 && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) || (ep.ld_bf16 % 4))) return HS_ERR_ALIGN;
   if (ep.resid && ((reinterpret_cast<uintptr_t>(ep.resid) & 15) || (ep.ld_resid % 4))) return HS_ERR_ALIGN;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, BK, 128);
+  int rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, 64, 128);
   if (rc != HS_OK) return rc;
-  rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, BK, 128);
+  rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, 64, 128);
   if (rc != HS_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -264,7 +273,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               cudaStream_t stream) {
   const char* e = std::getenv("HSENET_GEMM_1CTA");     // read per call so tests can flip it in-process
   const bool force_1cta = e != nullptr && e[0] == '1';
-  if (force_1cta || M <= 128) return gemm_bf16_1cta(A, lda, W, ldw, M, N, K, ep, stream);
+  if (force_1cta || M <= 128 || (K % 128) != 0) return gemm_bf16_1cta(A, lda, W, ldw, M, N, K, ep, stream);
   return gemm_bf16_2cta(A, lda, W, ldw, M, N, K, ep, stream);
 }
 

@@ -31,11 +31,12 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GFLOP_PER_VOLUME = {"c2": 1017.22, "c3": 1033.54}
-DEFAULT_BATCH = {"c2": 8, "c3": 32}
+GFLOP_PER_VOLUME = {"c2": 1017.22, "c3": 1033.54, "c4": 506.05}
+DEFAULT_BATCH = {"c2": 8, "c3": 32, "c4": 32}
 WORKLOAD_NAME = {
     "c2": "C2 dual encoder (ViT_stage1 + ViT_stage2/2E3) forward, bf16",
     "c3": "C3 dual encoder + two spatial packers -> [B,256,3072], bf16",
+    "c4": "C4 stage-1 CLIP image side: ViT_stage1 -> cls head -> packed all-gather of image/text embeddings -> logits",
 }
 
 
@@ -118,9 +119,24 @@ def make_inputs(B, rank, n_sets, pinned):
     return sets
 
 
+_c4_state = {}
+
+
 def run_step(enc, workload, x, s):
     if workload == "c2":
         return enc.vision_tower(x, s)                 # (feat_stage1 [B,2048,768], feat_stage2 [B,2048,768])
+    if workload == "c4":
+        import hsenet_b200 as H
+        if "head" not in _c4_state:
+            torch.manual_seed(1)
+            _c4_state["head"] = H.ClipImageHead().eval().requires_grad_(False).to(x.device)
+            g = torch.Generator().manual_seed(99)
+            _c4_state["text"] = torch.nn.functional.normalize(torch.randn(x.shape[0], 768, generator=g)).to(x.device)
+            _c4_state["scale"] = torch.tensor(1.0 / 0.07, device=x.device)
+        tokens, _ = enc.vision_tower.vision_tower_stage1(x)
+        emb = _c4_state["head"](tokens)                                    # [B_loc,768] unit-norm, fp32
+        _, lpi, _ = H.contrastive_logits(emb, _c4_state["text"], _c4_state["scale"])   # NCCL all-gather inside
+        return lpi                                                          # [B_global, B_global]
     return enc(x, s)                                  # [B,256,3072]
 
 
@@ -143,6 +159,9 @@ def cpu_reference_run(workload, threads, reps):
             t0 = time.perf_counter()
             if workload == "c2":
                 O.dual_tower(tsd, x, s)
+            elif workload == "c4":
+                O.vit_stage1({k[len("vision_tower_stage1."):]: v for k, v in tsd.items()
+                              if k.startswith("vision_tower_stage1.")}, x)
             else:
                 O.encode_images(tsd, p1, p2, x, s)
             dt = time.perf_counter() - t0
@@ -156,12 +175,23 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--batch", type=int, default=0, help="volumes per GPU per step (default: 8 for c2, 32 for c3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner from C) write to fd 1 too, so
+    # everything but the final line is routed to stderr.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
+        print(json.dumps(obj), flush=True)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -184,13 +214,13 @@ def main():
         t = statistics.median(times)
         v = 1.0 / t
         sample = f"1 volume per step, {len(times)} timed steps after 1 warm-up (median), fp32 eager PyTorch oracle port"
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "CT volumes/s encoded", "value": v, "unit": "volumes/s", "n_gpus": world,
             "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        })
         return
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -368,9 +398,9 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / t, "unit": "volumes/s", "cores": threads, "kind": "port",
                                 "sample": "1 volume per step, 2 timed steps after 1 warm-up (median), fp32 eager "
                                           "PyTorch oracle port of the reference's vit.py / packer"}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -34,13 +34,24 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof[idx_].b, st_);
 }
 
+bool first_use_on_device(unsigned char* slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  if (slot[dev]) return false;
+  slot[dev] = 1;
+  return true;
+}
+
 int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
+  static int cache[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  if (cache[dev] == 0) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = v > 0 ? v : 148;
+  }
+  return cache[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -274,11 +274,10 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
   CUtensorMap tm;
   const int rc = make_tmap_2d_bf16(&tm, qkv, 3 * kHidden, static_cast<uint64_t>(B) * S, 3 * kHidden, kHeadDim, 128);
   if (rc != HS_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned char attr_set[kMaxDevices] = {0};
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess)
       return HS_ERR_CUDA;
-    attr_set = true;
   }
   ProfScope prof(PROF_ATTENTION, 4.0 * B * kHeads * double(S) * S * kHeadDim, 2.0 * B * double(S) * 4 * kHidden,
                  stream);

@@ -183,15 +183,14 @@ int gemm_bf16_1cta(const void* A, int lda, const void* W, int ldw, int M, int N,
   if (rc != HS_OK) return rc;
   rc = make_tmap_2d_bf16(&tmB, W, K, N, ldw, BK, BN);
   if (rc != HS_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned char attr_set[kMaxDevices] = {0};
+  if (first_use_on_device(attr_set)) {
     bool ok = true;
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_F32_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     if (!ok) return HS_ERR_CUDA;
-    attr_set = true;
   }
   const int tiles = (N / BN) * ((M + BM - 1) / BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();

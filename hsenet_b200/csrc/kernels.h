@@ -47,6 +47,10 @@ struct ProfScope {
 };
 
 int num_sms();
+// true exactly once per (call site slot, current device): kernel attributes are per device, and one process may
+// drive several GPUs.  `slot` must point to a zero-initialised static array of kMaxDevices flags.
+constexpr int kMaxDevices = 64;
+bool first_use_on_device(unsigned char* slot);
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer);
 

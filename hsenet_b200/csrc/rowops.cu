@@ -545,12 +545,11 @@ template <typename OutT>
 int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn, int B, cudaStream_t stream) {
   if (B <= 0) return HS_OK;
   constexpr int smem = 2 * kNSlice * kHidden * 4;   // 196,608 B
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned char attr_set[kMaxDevices] = {0};
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(slice_xattn_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
       return HS_ERR_CUDA;
-    attr_set = true;
   }
   slice_xattn_kernel<OutT><<<dim3(kNPatch / kXaRowsPerCta, B), 256, smem, stream>>>(Q, KV, O, attn);
   count_launch();

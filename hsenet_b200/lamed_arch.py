@@ -39,6 +39,52 @@ def encode_images(self, images, text_feature=None, images_2d=None):
                               images_2d, out_dtype)
 
 
+def prepare_inputs_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images,
+                                  images_2d):
+    """Method-compatible replacement for LamedMetaForCausalLM.prepare_inputs_for_multimodal (lamed_arch.py:143-155).
+
+    The reference builds ``cat(embeds[:, :1], image_features, embeds[:, n+1:])`` (two full-tensor copies of
+    [B, L, 3072]); here the two packers' GEMM epilogues write their 128 tokens each directly into positions
+    1..256 of a copy of ``inputs_embeds``.  Same early-out as the reference when there
+    is no tower / no image / a single decode token (lamed_arch.py:148)."""
+    vision_tower = self.get_vision_tower()
+    if vision_tower is None or images is None or input_ids.shape[1] == 1:
+        return input_ids, position_ids, attention_mask, past_key_values, None, labels
+    m = self.get_model()
+    inputs_embeds = m.embed_tokens(input_ids)
+    inputs_embeds = splice_visual_tokens(m.get_vision_tower(), m.mm_projector, getattr(m, "mm_projector2", None),
+                                         inputs_embeds, images, images_2d)
+    return None, position_ids, attention_mask, past_key_values, inputs_embeds, labels
+
+
+def splice_visual_tokens(tower, mm_projector, mm_projector2, inputs_embeds, images, images_2d):
+    """inputs_embeds [B, L, D] -> new tensor whose positions 1 .. 256 hold the visual tokens."""
+    feats = tower(images, images_2d)
+    if not (isinstance(feats, tuple) and feats[-1].shape[1] == 2048):
+        # single-tower configurations: keep the reference's formulation
+        f = mm_projector(feats)
+        return torch.cat((inputs_embeds[:, :1, :], f.to(inputs_embeds.dtype), inputs_embeds[:, f.shape[1] + 1:, :]), 1)
+    second = mm_projector2 if mm_projector2 is not None else mm_projector
+    n1, n2 = mm_projector.proj_out_num, second.proj_out_num
+    B, L, D = inputs_embeds.shape
+    if L < 1 + n1 + n2:
+        raise ValueError(f"sequence of {L} tokens cannot hold {n1 + n2} visual tokens after the first token")
+    if D != mm_projector.out_dim:
+        raise ValueError(f"embedding width {D} != packer out_dim {mm_projector.out_dim}")
+    direct = inputs_embeds.dtype in (torch.float32, torch.bfloat16) and not (
+        rt.get_precision() == "fp32_verify" and inputs_embeds.dtype != torch.float32)
+    if direct:
+        out = inputs_embeds.detach().clone(memory_format=torch.contiguous_format)
+        mm_projector.forward_into(feats[0], out, 1)
+        second.forward_into(feats[1], out, 1 + n1)
+        return out
+    # fp16 (the reference's eval autocast): pack in the activation dtype, then one cast-copy into the slot
+    vis = encode_images_with(tower, mm_projector, mm_projector2, images, images_2d)
+    out = inputs_embeds.detach().clone(memory_format=torch.contiguous_format)
+    out[:, 1:1 + n1 + n2] = vis.to(out.dtype)
+    return out
+
+
 class HSENetVisualEncoder(nn.Module):
     """Dual tower + the two spatial packers, assembled the way LamedMetaModel.initialize_vision_modules does
     (lamed_arch.py:41-84).  ``forward(images, images_2d) -> [B,256,out_dim]``."""

@@ -131,3 +131,43 @@ def test_no_cpu_path_and_errors(cuda):
         m(torch.zeros(1, 1, 16, 256, 256, device=cuda))
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 1, 32, 256, 256, device=cuda))   # grad enabled + trainable params: no silent detach
+
+
+def test_splice_into_llm_embeddings(cuda):
+    """prepare_inputs_for_multimodal (lamed_arch.py:143-155).  The packers write straight into
+    positions 1..256 of the embedding sequence; result must equal the reference's cat(embeds[:, :1], feats, embeds[:, 257:])."""
+    import hsenet_b200 as H
+    torch.manual_seed(0)
+    enc = randomize_params(H.HSENetVisualEncoder(H.VisionConfig())).eval().requires_grad_(False).to(cuda)
+    x, s = synthetic_inputs(2, seed=3)
+    x, s = x.to(cuda), s.to(cuda)
+    L = 300
+
+    class FakeLM:
+        def __init__(self, dtype):
+            self.emb = torch.nn.Embedding(1000, 3072).to(cuda).to(dtype).requires_grad_(False)
+            self.mm_projector, self.mm_projector2 = enc.mm_projector, enc.mm_projector2
+        def get_model(self): return self
+        def get_vision_tower(self): return enc.vision_tower
+        def embed_tokens(self, ids): return self.emb(ids)
+
+    ids = torch.randint(0, 1000, (2, L), device=cuda)
+    for dtype in (torch.bfloat16, torch.float32, torch.float16):
+        lm = FakeLM(dtype)
+        with torch.no_grad(), H.precision("bf16"):
+            feats = H.encode_images(lm, x, None, s)                               # [2,256,3072] bf16
+            r = H.prepare_inputs_for_multimodal(lm, ids, None, None, None, None, x, s)
+            assert r[0] is None and r[4].shape == (2, L, 3072) and r[4].dtype == dtype
+            e = lm.embed_tokens(ids)
+            ref = torch.cat((e[:, :1], feats.to(dtype), e[:, 257:]), dim=1)        # the reference's formulation
+            if dtype == torch.float32:
+                # fp32 slot: the GEMM epilogue stores its fp32 accumulator instead of a bf16-rounded value
+                assert metrics(r[4][:, 1:257], feats)["max_rel"] < 5e-3
+                assert torch.equal(r[4][:, :1], e[:, :1]) and torch.equal(r[4][:, 257:], e[:, 257:])
+            else:
+                assert torch.equal(r[4], ref)
+            # decode step (one token) and missing image: passthrough like lamed_arch.py:148
+            r1 = H.prepare_inputs_for_multimodal(lm, ids[:, :1], None, None, None, None, x, s)
+            assert r1[0] is ids[:, :1] or torch.equal(r1[0], ids[:, :1])
+            assert r1[4] is None
+            assert H.prepare_inputs_for_multimodal(lm, ids, None, None, None, None, None, None)[4] is None

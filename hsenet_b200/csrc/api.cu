@@ -2,6 +2,7 @@
 // operator kernels.  No allocation, no synchronisation, no CPU compute: everything is enqueued on the caller's stream.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -32,6 +33,14 @@ ProfScope::~ProfScope() {
   if (idx_ < 0) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEventRecord(g_prof[idx_].b, st_);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("HSENET_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 bool first_use_on_device(unsigned char* slot) {

@@ -97,6 +97,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_prologue_done();      // everything above is independent of the previous kernel's output
 
   if (warp == 0) {
     if (lane == 0) {
@@ -281,7 +282,7 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
   }
   ProfScope prof(PROF_ATTENTION, 4.0 * B * kHeads * double(S) * S * kHeadDim, 2.0 * B * double(S) * 4 * kHidden,
                  stream);
-  attention_kernel<<<dim3((S + QT - 1) / QT, kHeads, B), ATT_THREADS, ATT_SMEM, stream>>>(tm, out, S);
+  launch_pdl(attention_kernel, dim3((S + QT - 1) / QT, kHeads, B), dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
 }

@@ -89,6 +89,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
   }
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// Every kernel that is launched with cudaLaunchAttributeProgrammaticStreamSerialization calls pdl_prologue_done()
+// right after its data-independent prologue (barrier init, TMEM alloc, descriptor prefetch): it first lets ITS
+// dependents start their own prologue, then blocks until the kernel it depends on has completed and flushed.
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- TMA -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

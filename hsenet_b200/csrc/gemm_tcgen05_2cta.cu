@@ -142,6 +142,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_prologue_done();      // everything above is independent of the previous kernel's output
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -258,10 +259,10 @@ int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N,
   const int grid = 2 * pairs;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 2.0 * (double(M) * K + double(N) * K + double(M) * N), stream);
   switch (epilogue_mode(ep)) {
-    case EPI_BF16: gemm_bf16_2cta_kernel<EPI_BF16><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
-    case EPI_BF16_GELU: gemm_bf16_2cta_kernel<EPI_BF16_GELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
-    case EPI_F32_RESID: gemm_bf16_2cta_kernel<EPI_F32_RESID><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
-    default: gemm_bf16_2cta_kernel<EPI_GENERIC><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16_GELU: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_F32_RESID: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    default: launch_pdl(gemm_bf16_2cta_kernel<EPI_GENERIC>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;

@@ -46,6 +46,25 @@ struct ProfScope {
   long idx_;
 };
 
+// Launch with the programmatic-stream-serialization attribute (PDL) unless HSENET_PDL=0.  Only for kernels that call
+// pdl_prologue_done() before touching global memory.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int num_sms();
 // true exactly once per (call site slot, current device): kernel attributes are per device, and one process may
 // drive several GPUs.  `slot` must point to a zero-initialised static array of kMaxDevices flags.

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, long rows,
                                                         OutT* __restrict__ out, long ldo,
                                                         OutT* __restrict__ out2, int seq) {
+  pdl_prologue_done();
   const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -469,8 +470,8 @@ int layernorm_rows(const float* x, long ldx, const float* gamma, const float* be
   if (rows <= 0) return HS_OK;
   if (!aligned16(x) || (ldx % 4) || (ldo % 4)) return HS_ERR_ALIGN;
   ProfScope prof(PROF_LAYERNORM, 0.0, double(rows) * kHidden * (4.0 + sizeof(OutT) * ((out != nullptr) + (out2 != nullptr))), stream);
-  layernorm_kernel<OutT><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, gamma, beta, rows, out,
-                                                                                    ldo, out2, seq);
+  launch_pdl(layernorm_kernel<OutT>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, x, ldx, gamma,
+             beta, rows, out, ldo, out2, seq);
   count_launch();
   return launch_status();
 }

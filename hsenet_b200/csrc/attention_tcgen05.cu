@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace hs {
 
 extern void count_launch();
@@ -40,6 +42,7 @@ constexpr int V_STAGES = 2;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int SUB_BYTES = KS * 128;        // 64 rows x 128 B
 constexpr int ATT_THREADS = 192;
+constexpr int kDefaultPoly = 2;      // measured: 2/8 -> -2.6 %, 4/8 -> +5 % (profiles/README.md)
 constexpr int TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
 constexpr int ATT_SMEM = (1 + K_STAGES + V_STAGES) * TILE_BYTES + 1024 + 256;
@@ -58,6 +61,49 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ---- packed fp32x2 helpers (sm_100 FFMA2 / FADD2: two fp32 lanes per issued instruction) -------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^y for two values on the FMA / ALU pipes (no MUFU): y = n + f with n = round(y), f in [-0.5, 0.5]; cubic for 2^f
+// (relative error < 7e-4, inside bf16's 2^-9 rounding); the exponent is patched in with integer adds.  Used for a
+// fraction of the exponentials: the MUFU pipe (16 ex2/clk/SM) is what bounds the softmax.
+__device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float& e1) {
+  y0 = fmaxf(y0, -126.0f);
+  y1 = fmaxf(y1, -126.0f);
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);        // 1.5 * 2^23
+  const uint64_t nmagic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t y = pack2(y0, y1);
+  const uint64_t t = add2(y, magic);                             // integer part lands in the low mantissa bits
+  const uint64_t n = add2(t, nmagic);
+  const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), y);            // f = y - n
+  uint64_t p = fma2(f, pack2(0.0555041f, 0.0555041f), pack2(0.2402265f, 0.2402265f));
+  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpack2(p, p0, p1);
+  unpack2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// POLY = how many of every 8 exponentials run on the FMA pipe instead of MUFU (0, 2 or 4)
+template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S) {
   extern __shared__ uint8_t smem_raw[];
@@ -205,12 +251,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         }
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const float e0 = ex2(fmaf(__uint_as_float(x[i + 0]), c, -m));
-          const float e1 = ex2(fmaf(__uint_as_float(x[i + 1]), c, -m));
-          rs0 += e0;
-          rs1 += e1;
-          pk[i >> 1] = pack_bf16x2(e0, e1);
+        for (int i = 0; i < 64; i += 8) {
+          float e[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) e[u] = fmaf(__uint_as_float(x[i + u]), c, -m);
+#pragma unroll
+          for (int u = 0; u < 8 - POLY; ++u) e[u] = ex2(e[u]);                       // MUFU pipe
+#pragma unroll
+          for (int u = 8 - POLY; u < 8; u += 2) exp2_poly2(e[u], e[u + 1], e[u], e[u + 1]);  // FMA pipe
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            rs0 += e[u];
+            rs1 += e[u + 1];
+            pk[(i + u) >> 1] = pack_bf16x2(e[u], e[u + 1]);
+          }
         }
         l = l * alpha + (rs0 + rs1);
         tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, pk);
@@ -277,12 +331,20 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
   if (rc != HS_OK) return rc;
   static unsigned char attr_set[kMaxDevices] = {0};
   if (first_use_on_device(attr_set)) {
-    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess)
-      return HS_ERR_CUDA;
+    bool ok = true;
+    ok &= cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    if (!ok) return HS_ERR_CUDA;
   }
   ProfScope prof(PROF_ATTENTION, 4.0 * B * kHeads * double(S) * S * kHeadDim, 2.0 * B * double(S) * 4 * kHidden,
                  stream);
-  launch_pdl(attention_kernel, dim3((S + QT - 1) / QT, kHeads, B), dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+  const char* e = std::getenv("HSENET_ATT_POLY");        // share of exponentials emulated on the FMA pipe (0 / 2 / 4 of 8)
+  const int poly = e != nullptr ? std::atoi(e) : kDefaultPoly;
+  const dim3 grid((S + QT - 1) / QT, kHeads, B);
+  if (poly >= 4) launch_pdl(attention_kernel<4>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+  else if (poly >= 2) launch_pdl(attention_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+  else launch_pdl(attention_kernel<0>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
 }

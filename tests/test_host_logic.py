@@ -124,3 +124,33 @@ def test_gather_features_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_graph_cache_keys_on_payload_and_workspace():
+    from hsenet_b200 import runtime as rt
+    gc = rt.GraphCache(max_entries=2)
+    assert gc.get(("k", 1), 10, 100) is None
+    ent = gc.put(("k", 1), 10, 100, {"graph": object()})
+    assert gc.get(("k", 1), 10, 100) is ent
+    assert gc.get(("k", 1), 11, 100) is None          # weights re-packed -> captured pointers are stale
+    assert gc.get(("k", 1), 10, 101) is None          # workspace re-allocated
+    gc.put(("k", 2), 10, 100, {})
+    gc.put(("k", 3), 10, 100, {})                      # evicts the oldest entry
+    assert len(gc.entries) == 2 and ("k", 1) not in gc.entries
+    assert isinstance(copy.deepcopy(gc), rt.GraphCache) and not copy.deepcopy(gc).entries
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints exactly ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c4",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "volumes/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]

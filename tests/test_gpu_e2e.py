@@ -171,3 +171,71 @@ def test_splice_into_llm_embeddings(cuda):
             assert r1[0] is ids[:, :1] or torch.equal(r1[0], ids[:, :1])
             assert r1[4] is None
             assert H.prepare_inputs_for_multimodal(lm, ids, None, None, None, None, None, None)[4] is None
+
+
+@pytest.mark.parametrize("remain,select", [("dual_vits", "patch"), ("dual_vits", "cls_patch"), ("3d_vit", "patch"),
+                                           ("2e3_vit", "cls_patch")])
+def test_tower_config_variants(cuda, remain, select):
+    """ViT3DTower_dual_encoders dispatch (vit.py:934-948): tuple vs single tensor, with / without the cls row."""
+    import hsenet_b200 as H
+    torch.manual_seed(0)
+    cfg = H.VisionConfig(select_feature=select, remain=remain)
+    tower = H.build_vision_tower(cfg)
+    for t in (tower.vision_tower_stage1, tower.vision_tower_stage2):      # keep the CPU oracle cheap: 1 block each
+        del t.blocks[1:]
+    tower = randomize_params(tower).eval().requires_grad_(False)
+    sd = cpu_state(tower)
+    x, s = synthetic_inputs(1, seed=11)
+    ref = O.dual_tower(sd, x, s, select_feature=select, remain=remain)
+    tower = tower.to(cuda)
+    with torch.no_grad(), H.precision("bf16"):
+        got = tower(x.to(cuda), s.to(cuda))
+    n = 2048 if select == "patch" else 2049
+    if remain == "dual_vits":
+        assert isinstance(got, tuple) and len(got) == 2
+        for g, r in zip(got, ref):
+            assert g.shape == (1, n, 768)
+            assert_bf16(g, r, f"{remain}/{select}")
+    else:
+        assert torch.is_tensor(got) and got.shape == (1, n, 768)
+        assert_bf16(got, ref, f"{remain}/{select}")
+    assert tower.hidden_size == 768 and tower.device.type == "cuda"
+
+
+def test_input_dtypes_layouts_and_output_dtype(cuda):
+    """Inputs arrive as fp32 in the reference even in bf16 runs, but fp16 / bf16 / non-contiguous tensors must work too
+    (SURVEY 8b 'Threading / devices'); output_dtype controls the returned dtype."""
+    import hsenet_b200 as H
+    torch.manual_seed(2)
+    m = randomize_params(H.ViT_stage2(num_layers=1, **GEOM)).eval().requires_grad_(False).to(cuda)
+    x, s = synthetic_inputs(2, seed=13)
+    x, s = x.to(cuda), s.to(cuda)
+    with torch.no_grad(), H.precision("bf16"):
+        base, _ = m(x, s)
+        # (a) non-contiguous volume (a strided view of a larger tensor) and a flattened [B, 32*768] slice tensor
+        big = torch.zeros(2, 1, 32, 256, 512, device=cuda)
+        big[..., ::2] = x
+        y, _ = m(big[..., ::2], s.reshape(2, -1))
+        assert torch.equal(y, base)
+        # (b) half-precision inputs: same as feeding their fp32 up-casts
+        y16, _ = m(x.half(), s.half())
+        yref, _ = m(x.half().float(), s.half().float())
+        assert torch.equal(y16, yref)
+        # (c) output dtype
+        m.output_dtype = torch.float32
+        y32, _ = m(x, s)
+        assert y32.dtype == torch.float32 and torch.equal(y32, base.float())
+        m.output_dtype = None
+        # (d) graphs off == graphs on (bitwise)
+        m.use_cuda_graph = False
+        yd, _ = m(x, s)
+        m.use_cuda_graph = True
+        assert torch.equal(yd, base)
+    # (e) weights updated in place (optimizer-style): the bf16 weight cache and the captured graph must follow
+    with torch.no_grad(), H.precision("bf16"):
+        m.blocks[0].mlp.linear2.weight.mul_(0.5)
+        y2, _ = m(x, s)
+        assert not torch.equal(y2, base)
+        m.blocks[0].mlp.linear2.weight.mul_(2.0)
+        y3, _ = m(x, s)
+        assert torch.equal(y3, base)

@@ -249,23 +249,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           alpha = ex2(m - tm);                           // m = -inf on the first step -> 0
           m = tm;
         }
-        float rs0 = 0.f, rs1 = 0.f;
+        // scale-subtract and row sum on packed fp32x2 (FFMA2 / FADD2: two lanes per issued instruction)
+        const uint64_t c2 = pack2(c, c), nm2 = pack2(-m, -m);
+        uint64_t rs2 = pack2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 64; i += 8) {
           float e[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) e[u] = fmaf(__uint_as_float(x[i + u]), c, -m);
+          for (int u = 0; u < 8; u += 2)
+            unpack2(fma2(pack2(__uint_as_float(x[i + u]), __uint_as_float(x[i + u + 1])), c2, nm2), e[u], e[u + 1]);
 #pragma unroll
-          for (int u = 0; u < 8 - POLY; ++u) e[u] = ex2(e[u]);                       // MUFU pipe
+          for (int u = 0; u < 8 - POLY; ++u) e[u] = ex2(e[u]);                                        // MUFU pipe
 #pragma unroll
-          for (int u = 8 - POLY; u < 8; u += 2) exp2_poly2(e[u], e[u + 1], e[u], e[u + 1]);  // FMA pipe
+          for (int u = 8 - POLY; u < 8; u += 2) exp2_poly2(e[u], e[u + 1], e[u], e[u + 1]);            // FMA pipe
 #pragma unroll
           for (int u = 0; u < 8; u += 2) {
-            rs0 += e[u];
-            rs1 += e[u + 1];
+            rs2 = add2(rs2, pack2(e[u], e[u + 1]));
             pk[(i + u) >> 1] = pack_bf16x2(e[u], e[u + 1]);
           }
         }
+        float rs0, rs1;
+        unpack2(rs2, rs0, rs1);
         l = l * alpha + (rs0 + rs1);
         tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, pk);
       }

@@ -280,6 +280,8 @@ def main():
         # (direct launches: the per-launch event hooks live in the library's launchers, which graph replays bypass)
         for tw in (enc.vision_tower.vision_tower_stage1, enc.vision_tower.vision_tower_stage2):
             tw.use_cuda_graph = False
+        concurrent = enc.vision_tower.concurrent_towers
+        enc.vision_tower.concurrent_towers = False      # one stream: per-launch event times must not overlap
         lib.hsenet_profile_start()
         for i in range(K):
             run_step(enc, args.workload, *dev_sets[i % n_sets])
@@ -287,6 +289,7 @@ def main():
         _lib.check(lib.hsenet_profile_stop(ms, fl, by, ln), "profile_stop")
         for tw in (enc.vision_tower.vision_tower_stage1, enc.vision_tower.vision_tower_stage2):
             tw.use_cuda_graph = True
+        enc.vision_tower.concurrent_towers = concurrent
 
         # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region ------------------------------------
         e2e = None

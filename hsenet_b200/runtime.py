@@ -71,6 +71,18 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_side_streams: dict = {}
+
+
+def side_stream(device: torch.device) -> "torch.cuda.Stream":
+    """One extra stream per device for work that runs beside the caller's stream (the second encoder of the tower)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = _side_streams[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
 def require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(

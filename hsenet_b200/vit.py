@@ -14,6 +14,7 @@ The modules hold parameters only; ``forward`` runs entirely inside libhsenet_sm1
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections.abc import Sequence
 
 import torch
@@ -220,7 +221,7 @@ class _ViTBase(nn.Module):
         want_hidden = self.return_hidden_states and len(self.blocks) > 0
         pc = rt.precision_code(prec)
         nbytes = lib.hsenet_vit_workspace_bytes(B, pc, self._stage)
-        ws = rt.workspace(dev, nbytes, "vit")
+        ws = rt.workspace(dev, nbytes, f"vit_stage{self._stage}")   # one per stage: the dual tower runs them concurrently
 
         def alloc_outputs():
             tok = torch.empty(B, SEQ, HIDDEN, dtype=act, device=dev)
@@ -344,12 +345,17 @@ class ViT3DTower_dual_encoders(nn.Module):
                   spatial_dims=len(self.config.patch_size), classification=True)
         self.vision_tower_stage1 = ViT_stage1(**kw)
         self.vision_tower_stage2 = ViT_stage2(**kw)
+        #: run the two (independent) encoders on two streams so that the partial last wave of every kernel of
+        #: one encoder is filled by CTAs of the other (5.5 waves of attention CTAs, 2.6 waves of fc2 tiles at B = 8)
+        self.concurrent_towers = os.environ.get("HSENET_CONCURRENT_TOWERS", "1") != "0"
 
     def forward(self, images, images_2d):
         t = self.remain_2d3d_ViT_type
         if self.select_feature not in ("patch", "cls_patch"):
             raise ValueError(f"Unexpected select feature: {self.select_feature}")
         feats = []
+        if t == "dual_vits" and self.concurrent_towers and images.is_cuda:
+            return self._forward_concurrent(images, images_2d)
         # the reference always runs both encoders (vit.py:928-929); skipping the unused one changes no result
         if t in ("dual_vits", "3d_vit"):
             tok, _ = self.vision_tower_stage1(images)
@@ -362,6 +368,21 @@ class ViT3DTower_dual_encoders(nn.Module):
         if t in ("3d_vit", "2e3_vit"):
             return feats[0]
         return None
+
+    def _forward_concurrent(self, images, images_2d):
+        dev = images.device
+        cur = torch.cuda.current_stream(dev)
+        side = rt.side_stream(dev)
+        side.wait_stream(cur)                       # images / weights produced on the caller's stream
+        with torch.cuda.stream(side):
+            tok1, _ = self.vision_tower_stage1(images)
+            f1 = self.vision_tower_stage1.last_patch_tokens if self.select_feature == "patch" else tok1
+        tok2, _ = self.vision_tower_stage2(images, images_2d)
+        f2 = self.vision_tower_stage2.last_patch_tokens if self.select_feature == "patch" else tok2
+        cur.wait_stream(side)
+        for t in (tok1, f1, self.vision_tower_stage1.last_patch_tokens):
+            t.record_stream(cur)                    # allocated on the side stream, consumed on the caller's
+        return f1, f2
 
     @property
     def dtype(self):

@@ -154,8 +154,10 @@ def _attn_ref(qkv, B, S):
     return (att @ v).permute(0, 2, 1, 3).reshape(B * S, 768)
 
 
+# 2049 / 257: one scalar tail key + one scalar tail query row; 130 / 2050: two of each; 66: tail keys only;
+# 131 / 192 / 1: remainders that take the masked last step and a partial last query tile
 @pytest.mark.parametrize("B,S,scale", [(2, 2049, 1.0), (1, 2049, 4.0), (3, 128, 2.0), (2, 130, 1.0), (1, 1, 1.0),
-                                       (1, 257, 8.0)])
+                                       (1, 257, 8.0), (2, 66, 2.0), (1, 131, 1.0), (2, 192, 3.0), (1, 2050, 2.0)])
 def test_attention_bf16(lib, cuda, B, S, scale):
     from hsenet_b200 import _lib
     g = torch.Generator().manual_seed(S + B)

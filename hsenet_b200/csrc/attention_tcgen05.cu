@@ -56,6 +56,30 @@ struct AttBarriers {
   uint32_t tmem_base;
 };
 
+// Trace build only (HSENET_NVCC_EXTRA=-DHSENET_ATT_TRACE, tools/attn_trace.py): per-phase clock64 sums of one softmax
+// warp and of the two issuing threads of CTA 0.  A clock read does not wait for earlier asynchronous instructions to
+// COMPLETE, only to issue: a slot also collects stalls caused by what was issued just before it.
+#ifdef HSENET_ATT_TRACE
+__device__ unsigned long long g_att_trace[48];   // [0,16) softmax warp 2, [16,32) Q K^T issuer, [32,48) P V issuer
+#define ATT_TR(i)                        \
+  do {                                   \
+    const long long _n = clock64();      \
+    tr[i] += _n - tlast;                 \
+    tlast = _n;                          \
+  } while (0)
+#define ATT_TR_DECL long long tr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tlast = clock64(); const long long tstart = tlast
+#define ATT_TR_DUMP(base)                                                              \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {                         \
+    for (int i = 0; i < 10; ++i) g_att_trace[(base) + i] = tr[i];                      \
+    g_att_trace[(base) + 14] = clock64() - tstart;                                     \
+    g_att_trace[(base) + 15] = nsub;                                                   \
+  }
+#else
+#define ATT_TR(i)
+#define ATT_TR_DECL
+#define ATT_TR_DUMP(base)
+#endif
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -165,11 +189,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     } else if (lane == 1) {
       // ===================== P V issuer =====================
       constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);    // O[128q x 64d] += P V (V MN-major)
+      ATT_TR_DECL;
       for (int t = 0; t < nsub; ++t) {
         const int bsel = t & 1, j = t >> 1, vs = j % V_STAGES;
         if (bsel == 0) mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+        ATT_TR(0);
         mbar_wait(&bars->p_full[bsel], (t >> 1) & 1);       // softmax t done: P[bsel] stored, O rescaled if needed
         tc_fence_after();
+        ATT_TR(1);
         const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + bsel * SUB_BYTES));
 #pragma unroll
         for (int k = 0; k < KS / 16; ++k) {
@@ -177,9 +204,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           umma_ts(tmem_base + COL_O, tmem_base + COL_P + bsel * 32 + 8 * k, vdesc + 128 * k, idesc_pv,
                   (t | k) != 0 ? 1u : 0u);
         }
+        ATT_TR(2);
         tc_commit(&bars->pv_done[bsel]);
         if (bsel == 1 || t == nsub - 1) tc_commit(&bars->v_empty[vs]);      // V tile fully consumed
+        ATT_TR(3);
       }
+      ATT_TR_DUMP(32);
     }
   } else if (warp == 1) {
     // ===================== Q K^T issuer =====================
@@ -187,22 +217,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
       mbar_wait(&bars->q_full, 0);
+      ATT_TR_DECL;
       for (int t = 0; t < nsub; ++t) {
         const int bsel = t & 1, j = t >> 1, ks = j % K_STAGES;
         if (bsel == 0) mbar_wait(&bars->k_full[ks], (j / K_STAGES) & 1);
+        ATT_TR(0);
         if (t >= 2) {
           const uint32_t par = ((t >> 1) - 1) & 1;
           mbar_wait(&bars->s_free[bsel], par);     // step t-2 holds its scores in registers: S[bsel] may be overwritten
           mbar_wait(&bars->pv_done[bsel], par);    // P V (t-2) retired: P[bsel] may be overwritten by step t
         }
         tc_fence_after();
+        ATT_TR(1);
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + bsel * SUB_BYTES));
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_ss(tmem_base + COL_S + bsel * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        ATT_TR(2);
         tc_commit(&bars->s_full[bsel]);
         if (bsel == 1 || t == nsub - 1) tc_commit(&bars->k_empty[ks]);      // K tile fully consumed
+        ATT_TR(3);
       }
+      ATT_TR_DUMP(16);
     }
   } else {
     // ===================== softmax / correction / epilogue warps =====================
@@ -213,6 +249,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     const float c = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
     float m = -INFINITY;                                 // running reference max (log2 domain, already scaled)
     float l = 0.f;
+    ATT_TR_DECL;
     // one 64-key step; MASKED (compile time) only for a last step that runs past the end of the sequence -- kept out
     // of the main loop on purpose: left as a run-time test the compiler turns the 64 per-key checks into selects that
     // execute on EVERY step (195 of ~530 instructions per step in the first version)
@@ -220,6 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       const int bsel = t & 1;
       mbar_wait(&bars->s_full[bsel], (t >> 1) & 1);      // S[bsel] ready and P[bsel] free
       tc_fence_after();
+      ATT_TR(0);
       uint32_t x[64];
       uint32_t pk[32];
       float alpha = 1.f;
@@ -228,10 +266,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         tmem_ld32(tmem_base + lane_base + COL_S + bsel * KS + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
         tmem_ld_wait();
       }
+      ATT_TR(1);
       // the scores are in registers: the Q K^T issuer may refill S[bsel] (for step t+2) while we exponentiate
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_free[bsel]);
+      ATT_TR(2);
       if (warp_live) {
         const int kbase = t * KS;
         if constexpr (decltype(masked)::value) {         // last step: mask keys past the sequence end
@@ -253,6 +293,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           alpha = ex2(m - tm);                           // m = -inf on the first step -> 0
           m = tm;
         }
+        ATT_TR(3);
         // scale-subtract and row sum on packed fp32x2 (FFMA2 / FADD2: two lanes per issued instruction)
         const uint64_t c2 = pack2(c, c), nm2 = pack2(-m, -m);
         uint64_t rs2 = pack2(0.f, 0.f);
@@ -275,7 +316,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         float rs0, rs1;
         unpack2(rs2, rs0, rs1);
         l = l * alpha + (rs0 + rs1);
+        ATT_TR(4);
         tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, pk);
+        ATT_TR(5);
       }
       // O correction (rare after the first steps): P V (t-1) must have retired before O is rescaled
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
@@ -291,14 +334,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           tmem_st32(tmem_base + lane_base + COL_O + ch * 32, o);
         }
       }
+      ATT_TR(6);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
+      ATT_TR(7);
     };
     const bool ragged = (S % KS) != 0;
     for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
     if (ragged) softmax_step(nsub - 1, std::true_type{});
+    if (warp == 2 && lane == 0) { ATT_TR_DUMP(0); }
     // ---- epilogue: O / l -> bf16 -> out[b*S + qi, h*64 .. h*64+63] -----------------------------------------------
     if (nsub >= 2) mbar_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
     mbar_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
@@ -361,3 +407,9 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
 }
 
 }  // namespace hs
+
+#ifdef HSENET_ATT_TRACE
+extern "C" int hsenet_debug_att_trace(unsigned long long* host48) {
+  return cudaMemcpyFromSymbol(host48, hs::g_att_trace, sizeof(unsigned long long) * 48) == cudaSuccess ? 0 : -4;
+}
+#endif

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsenet_sm100a.so")
+LIB_PATH = os.environ.get("HSENET_LIB_PATH") or os.path.join(_HERE, "libhsenet_sm100a.so")   # override: A/B of two builds
 
 OK = 0
 ERR_SHAPE, ERR_ALIGN, ERR_CUDA, ERR_ARG, ERR_DRIVER = -1, -2, -3, -4, -5
@@ -21,7 +21,8 @@ vp = C.c_void_p
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("w_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
-                                  "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+                                  "ln1_g", "ln1_b", "ln2_g", "ln2_b",
+                                  "w_qkv_ln", "cs_qkv", "b_qkv_ln", "w_fc1_ln", "cs_fc1", "b_fc1_ln")]
 
 
 class VitWeights(C.Structure):
@@ -63,6 +64,7 @@ SIGNATURES = {
     "hsenet_patch_gather_map": (C.c_int, [vp, vp]),
     "hsenet_packer_window_map": (C.c_int, [vp, vp]),
     "hsenet_cast_bf16": (C.c_int, [vp, vp, C.c_long, vp]),
+    "hsenet_fold_layernorm": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
 }
 
 _lib = None

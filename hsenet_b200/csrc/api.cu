@@ -9,6 +9,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+#include <type_traits>
+
 namespace hs {
 
 static std::atomic<uint64_t> g_launches{0};
@@ -134,6 +137,8 @@ struct Prec<float> {
   }
 };
 
+inline bool ln_fold_disabled() { return false; }   // folding is selected by the caller: it supplies the folded weights
+
 template <typename T>
 inline void set_act_out(GemmEpilogue& ep, T* p, int ld) {
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p);
@@ -146,6 +151,9 @@ inline void set_act_out(GemmEpilogue& ep, T* p, int ld) {
     if (_rc != HS_OK) return _rc;    \
   } while (0)
 
+constexpr int kMaxFusedLayers = 32;    // statistics slots in the workspace; deeper layers keep the LayerNorm kernel
+constexpr float kLnEps = 1e-5f;        // nn.LayerNorm default (same constant as layernorm_rows)
+
 // ---- ViT workspace layout -----------------------------------------------------------------------------------
 template <typename T>
 struct VitWs {
@@ -156,6 +164,8 @@ struct VitWs {
   T* H;          // [M,3072]  (aliased by the im2col patches [Mp,1024] and, stage 2, XP fp32 [Mp,768])
   T* S16;        // [B*32,768]   slice features as act
   float* SKV;    // [B*32,1536]  Wk|Wv of the slice features
+  float2* STATS; // [2*kMaxFusedLayers, M]  (sum, sum of squares) per residual row for the LayerNorms folded into GEMMs
+  size_t stats_bytes;
   size_t total;
   VitWs(void* base, int B) {
     const size_t M = static_cast<size_t>(B) * kSeq;
@@ -167,6 +177,8 @@ struct VitWs {
     H = b.take<T>(M * kMlp);
     S16 = b.take<T>(static_cast<size_t>(B) * kNSlice * kHidden);
     SKV = b.take<float>(static_cast<size_t>(B) * kNSlice * 2 * kHidden);
+    stats_bytes = 2 * static_cast<size_t>(kMaxFusedLayers) * M * sizeof(float2);
+    STATS = b.take<float2>(2 * static_cast<size_t>(kMaxFusedLayers) * M);
     total = b.off;
   }
 };
@@ -229,30 +241,68 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
   HS_TRY(write_cls_rows(ws.X, w->cls_token, B, kSeq, st));
 
   // 12 x MONAI TransformerBlock (vit.py:463-466): x += attn(norm1(x)); x += mlp(norm2(x))
+  // bf16 path with gain-folded weights supplied: norm2 of every layer and norm1 of layers >= 1 are folded into the
+  // GEMMs around them (gemm_epilogue.cuh) -- the GEMM that produces x also writes bf16(x) into XN and the row
+  // statistics, the consuming GEMM runs on XN with W' = gamma (.) W and normalises in its epilogue.
+  constexpr bool kCanFold = std::is_same<T, __nv_bfloat16>::value;
+  auto folds_ln1 = [&](int l) {
+    return kCanFold && l >= 1 && l < w->num_layers && l < kMaxFusedLayers && w->blocks_host[l].w_qkv_ln != nullptr &&
+           w->blocks_host[l].cs_qkv != nullptr && w->blocks_host[l].b_qkv_ln != nullptr && !ln_fold_disabled();
+  };
+  auto folds_ln2 = [&](int l) {
+    return kCanFold && l < kMaxFusedLayers && w->blocks_host[l].w_fc1_ln != nullptr &&
+           w->blocks_host[l].cs_fc1 != nullptr && w->blocks_host[l].b_fc1_ln != nullptr && !ln_fold_disabled();
+  };
+  bool any_fold = false;
+  for (int l = 0; l < w->num_layers; ++l) any_fold |= folds_ln1(l) || folds_ln2(l);
+  if (any_fold && cudaMemsetAsync(ws.STATS, 0, ws.stats_bytes, st) != cudaSuccess) return HS_ERR_CUDA;
   for (int l = 0; l < w->num_layers; ++l) {
     const hsenet_block_weights& bw = w->blocks_host[l];
-    HS_TRY(layernorm_rows<T>(ws.X, kHidden, bw.ln1_g, bw.ln1_b, M, ws.XN, kHidden, nullptr, kSeq, st));
+    float2* stats1 = ws.STATS + static_cast<size_t>(2 * l) * M;          // rows entering norm1 of layer l
+    float2* stats2 = ws.STATS + static_cast<size_t>(2 * l + 1) * M;      // rows entering norm2 of layer l
     {
       GemmEpilogue ep;   // qkv, no bias
       set_act_out(ep, ws.QKV, 3 * kHidden);
-      HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
+      if (folds_ln1(l)) {
+        ep.bias = bw.b_qkv_ln; ep.colsum = bw.cs_qkv; ep.stats_in = stats1;
+        ep.ln_inv_dim = 1.0f / kHidden; ep.ln_eps = kLnEps;
+        HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv_ln, kHidden, M, 3 * kHidden, kHidden, ep, st));
+      } else {
+        HS_TRY(layernorm_rows<T>(ws.X, kHidden, bw.ln1_g, bw.ln1_b, M, ws.XN, kHidden, nullptr, kSeq, st));
+        HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
+      }
     }
     HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, B, kSeq, st));
     {
       GemmEpilogue ep;   // out_proj + residual
       ep.bias = bw.b_out; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
+      if (folds_ln2(l)) {
+        set_act_out(ep, ws.XN, kHidden);
+        ep.stats_out = stats2;
+      }
       HS_TRY(Prec<T>::gemm(ws.ATT, kHidden, bw.w_out, kHidden, M, kHidden, kHidden, ep, st));
     }
-    HS_TRY(layernorm_rows<T>(ws.X, kHidden, bw.ln2_g, bw.ln2_b, M, ws.XN, kHidden, nullptr, kSeq, st));
     {
       GemmEpilogue ep;   // linear1 + exact GELU
-      ep.bias = bw.b_fc1; ep.gelu = 1;
+      ep.gelu = 1;
       set_act_out(ep, ws.H, kMlp);
-      HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_fc1, kHidden, M, kMlp, kHidden, ep, st));
+      if (folds_ln2(l)) {
+        ep.bias = bw.b_fc1_ln; ep.colsum = bw.cs_fc1; ep.stats_in = stats2;
+        ep.ln_inv_dim = 1.0f / kHidden; ep.ln_eps = kLnEps;
+        HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_fc1_ln, kHidden, M, kMlp, kHidden, ep, st));
+      } else {
+        ep.bias = bw.b_fc1;
+        HS_TRY(layernorm_rows<T>(ws.X, kHidden, bw.ln2_g, bw.ln2_b, M, ws.XN, kHidden, nullptr, kSeq, st));
+        HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_fc1, kHidden, M, kMlp, kHidden, ep, st));
+      }
     }
     {
       GemmEpilogue ep;   // linear2 + residual
       ep.bias = bw.b_fc2; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
+      if (folds_ln1(l + 1)) {
+        set_act_out(ep, ws.XN, kHidden);
+        ep.stats_out = ws.STATS + static_cast<size_t>(2 * (l + 1)) * M;
+      }
       HS_TRY(Prec<T>::gemm(ws.H, kMlp, bw.w_fc2, kMlp, M, kHidden, kMlp, ep, st));
     }
     if (hidden != nullptr) {
@@ -565,6 +615,14 @@ int hsenet_packer_window_map(int32_t* out, hsenet_stream_t stream) {
 int hsenet_cast_bf16(const float* in, void* out, long n, hsenet_stream_t stream) {
   if (in == nullptr || out == nullptr) return HSENET_ERR_ARG;
   return cast_rows<__nv_bfloat16>(in, static_cast<__nv_bfloat16*>(out), n, static_cast<cudaStream_t>(stream));
+}
+int hsenet_fold_layernorm(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
+                          void* w_folded_bf16, float* colsum, float* bias_folded, hsenet_stream_t stream) {
+  if (w == nullptr || gamma == nullptr || beta == nullptr || w_folded_bf16 == nullptr || colsum == nullptr ||
+      bias_folded == nullptr || N < 0 || K < 0)
+    return HSENET_ERR_ARG;
+  return fold_layernorm(w, gamma, beta, bias, N, K, static_cast<__nv_bfloat16*>(w_folded_bf16), colsum, bias_folded,
+                        static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

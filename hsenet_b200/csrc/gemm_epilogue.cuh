@@ -10,6 +10,12 @@
 //   EPI_BF16_GELU  out_bf16 = gelu(acc + bias)                  (MLP linear1, packer proj_mpls.0)
 //   EPI_F32_RESID  out_f32  = acc + bias + resid (may alias)    (attention out_proj, MLP linear2, output_linear)
 //   EPI_GENERIC    everything GemmEpilogue can express (row remap, positional embedding, dual outputs)
+// LayerNorm between two GEMMs is folded into their epilogues instead of running as a kernel of its own (which re-read
+// the fp32 residual stream, 50 MB per call at batch 8):  LN(x) W^T = rstd (x W'^T) - rstd mu colsum(W') + (W beta + b)
+// with W' = gamma (.) W, so
+//   EPI_F32_RESID_LN   the producer also writes a bf16 copy of its output rows (the next GEMM's A operand) and adds each
+//                      row's (sum, sum of squares) -- taken from the fp32 values -- into stats_out;
+//   EPI_BF16_LN, EPI_BF16_GELU_LN   the consumer multiplies by W' and applies the per-row scale / shift from stats_in.
 // All residual loads of a 32x32 block are issued before the first store (the residual aliases the output, so the
 // compiler cannot hoist them itself): this keeps the fp32 residual stream HBM-bound instead of latency-bound.
 #pragma once
@@ -18,18 +24,23 @@
 
 namespace hs {
 
-enum : int { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32_RESID = 2, EPI_GENERIC = 3 };
+enum : int { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32_RESID = 2, EPI_GENERIC = 3, EPI_BF16_LN = 4, EPI_BF16_GELU_LN = 5,
+              EPI_F32_RESID_LN = 6 };
 
 constexpr int EPI_WARP_BYTES = 32 * 128;   // one 32x32 fp32 block per epilogue warp
 
 __host__ inline int epilogue_mode(const GemmEpilogue& ep) {
   const bool plain = ep.rows_per_group == 0 && ep.row_add == nullptr;
-  if (plain && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.resid == nullptr)
+  if (plain && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.resid == nullptr && ep.stats_out == nullptr) {
+    if (ep.stats_in != nullptr) return ep.gelu ? EPI_BF16_GELU_LN : EPI_BF16_LN;
     return ep.gelu ? EPI_BF16_GELU : EPI_BF16;
-  if (plain && ep.out_f32 != nullptr && ep.out_bf16 == nullptr && ep.resid != nullptr && !ep.gelu &&
-      ep.bias != nullptr)
-    return EPI_F32_RESID;
-  return EPI_GENERIC;
+  }
+  if (plain && ep.out_f32 != nullptr && ep.resid != nullptr && !ep.gelu && ep.bias != nullptr &&
+      ep.stats_in == nullptr) {
+    if (ep.out_bf16 != nullptr && ep.stats_out != nullptr) return EPI_F32_RESID_LN;
+    if (ep.out_bf16 == nullptr && ep.stats_out == nullptr) return EPI_F32_RESID;
+  }
+  return EPI_GENERIC;     // (does not implement the LayerNorm fields: callers must hit one of the cases above)
 }
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7):
@@ -59,17 +70,87 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+// LayerNorm-consuming modes: rstd and -mean*rstd of the 8 rows this lane handles in the readback (row_base + (lane>>3)
+// + 4*it).  The epilogue runs BEHIND the tensor pipe in the K = 768 GEMMs, so the statistics are loaded one tile ahead
+// (epilogue_ln_load for tile i+1 is issued before the slab of tile i is processed) and only turned into coefficients
+// (epilogue_ln_coeffs) when their tile starts: an L2 round trip per tile on the critical path cost 11 % of the kernel.
+template <int MODE>
+__device__ __forceinline__ void epilogue_ln_load(const GemmEpilogue& ep, int row_base, int M, int lane, float2 (&sq)[8]) {
+  if constexpr (MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + (lane >> 3) + 4 * it;
+      sq[it] = make_float2(0.f, 1.f);
+      if (row < M) sq[it] = __ldg(ep.stats_in + row);
+    }
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void epilogue_ln_coeffs(const GemmEpilogue& ep, const float2 (&sq)[8], float (&ln_a)[8],
+                                                   float (&ln_b)[8]) {
+  if constexpr (MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float mean = sq[it].x * ep.ln_inv_dim;
+      const float var = fmaxf(sq[it].y * ep.ln_inv_dim - mean * mean, 0.f);
+      ln_a[it] = rsqrtf(var + ep.ln_eps);
+      ln_b[it] = -mean * ln_a[it];
+    }
+  }
+}
+
 template <int MODE, typename Release>
 __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t taddr, uint32_t stage, int row_base,
-                                              int col_base, int M, int N, int lane, Release&& release) {
+                                              int col_base, int M, int N, int lane, const float (&ln_a)[8],
+                                              const float (&ln_b)[8], Release&& release) {
   const int sub_row = lane >> 3;         // 0..3   readback: 4 rows per pass
   const int sub_chunk = lane & 7;        // 16-byte column chunk owned by this lane in the readback
   const uint32_t wr_base = stage + lane * 128;
   const int wr_sw = lane & 7;
+  constexpr bool LN_IN = MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN;
+  constexpr bool LN_OUT = MODE == EPI_F32_RESID_LN;
+  // per-lane rows of the readback are row_base + sub_row + 4*it
+  float st_s[LN_OUT ? 8 : 1], st_q[LN_OUT ? 8 : 1];      // producer: partial sum / sum of squares over this slab
+  if constexpr (LN_OUT) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) st_s[it] = st_q[it] = 0.f;
+  }
+  // residual modes: the residual of chunk c+1 is requested before chunk c is processed (different addresses from the
+  // stores of chunk c, so the in-place update stays safe); otherwise every chunk exposes a full HBM/L2 round trip
+  constexpr bool RESID = MODE == EPI_F32_RESID || LN_OUT;
+  float4 rs_next[RESID ? 8 : 1];
+  auto load_resid = [&](int chunk, float4 (&dst)[RESID ? 8 : 1]) {
+    if constexpr (RESID) {
+      const float* rp = ep.resid + static_cast<long>(row_base + sub_row) * ep.ld_resid + col_base + chunk * 32 + sub_chunk * 4;
+      const long rstep = 4L * ep.ld_resid;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_base + sub_row + 4 * it < M) dst[it] = *reinterpret_cast<const float4*>(rp + it * rstep);
+      }
+    }
+  };
+  load_resid(0, rs_next);
+  // per-column vectors (bias, colsum) are likewise requested one chunk ahead
+  float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f), cs_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_cols = [&](int chunk) {
+    const int c = col_base + chunk * 32 + sub_chunk * 4;
+    if (ep.bias != nullptr) bias_next = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+    if constexpr (LN_IN) cs_next = __ldg(reinterpret_cast<const float4*>(ep.colsum + c));
+  };
 #pragma unroll 1
   for (int chunk = 0; chunk < 4; ++chunk) {
     uint32_t v[32];
     tmem_ld32(taddr + chunk * 32, v);
+    load_cols(chunk);
+    const float4 bias4 = bias_next;
+    [[maybe_unused]] const float4 cs4 = cs_next;
+    float4 rs[RESID ? 8 : 1];
+    if constexpr (RESID) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) rs[it] = rs_next[it];
+      if (chunk < 3) load_resid(chunk + 1, rs_next);
+    }
     tmem_ld_wait();
     if (chunk == 3) release();           // last TMEM read of this slab: the accumulator stage can be reused
     __syncwarp();                        // previous block fully read back before it is overwritten
@@ -78,20 +159,25 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
       sts128(wr_base + ((c ^ wr_sw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
     __syncwarp();
     const int col = col_base + chunk * 32 + sub_chunk * 4;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
     const int row_first = row_base + sub_row;            // rows row_first + 4*it
     const uint32_t rd_base = stage + sub_row * 128;      // + it*512, chunk swizzled by (row & 7)
 
-    if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU) {
+    if constexpr (MODE == EPI_BF16 || MODE == EPI_BF16_GELU || LN_IN) {
       __nv_bfloat16* o = ep.out_bf16 + static_cast<long>(row_first) * ep.ld_bf16 + col;
       const long step = 4L * ep.ld_bf16;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + sub_row;
         float4 x = lds128(rd_base + it * 512 + ((sub_chunk ^ (r & 7)) << 4));
-        x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-        if constexpr (MODE == EPI_BF16_GELU) {
+        if constexpr (LN_IN) {
+          x.x = fmaf(x.x, ln_a[it], fmaf(ln_b[it], cs4.x, bias4.x));
+          x.y = fmaf(x.y, ln_a[it], fmaf(ln_b[it], cs4.y, bias4.y));
+          x.z = fmaf(x.z, ln_a[it], fmaf(ln_b[it], cs4.z, bias4.z));
+          x.w = fmaf(x.w, ln_a[it], fmaf(ln_b[it], cs4.w, bias4.w));
+        } else {
+          x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+        }
+        if constexpr (MODE == EPI_BF16_GELU || MODE == EPI_BF16_GELU_LN) {
           x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w);
         }
         if (row_first + 4 * it < M) {
@@ -101,22 +187,31 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
           *reinterpret_cast<uint2*>(o + it * step) = pk;
         }
       }
-    } else if constexpr (MODE == EPI_F32_RESID) {
-      const float* rp = ep.resid + static_cast<long>(row_first) * ep.ld_resid + col;
+    } else if constexpr (MODE == EPI_F32_RESID || LN_OUT) {
       float* o = ep.out_f32 + static_cast<long>(row_first) * ep.ld_f32 + col;
-      const long rstep = 4L * ep.ld_resid, ostep = 4L * ep.ld_f32;
-      float4 rs[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_first + 4 * it < M) rs[it] = *reinterpret_cast<const float4*>(rp + it * rstep);
+      const long ostep = 4L * ep.ld_f32;
+      __nv_bfloat16* ob = nullptr;
+      long bstep = 0;
+      if constexpr (LN_OUT) {
+        ob = ep.out_bf16 + static_cast<long>(row_first) * ep.ld_bf16 + col;
+        bstep = 4L * ep.ld_bf16;
       }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + sub_row;
         float4 x = lds128(rd_base + it * 512 + ((sub_chunk ^ (r & 7)) << 4));
         x.x += bias4.x + rs[it].x; x.y += bias4.y + rs[it].y; x.z += bias4.z + rs[it].z; x.w += bias4.w + rs[it].w;
-        if (row_first + 4 * it < M) *reinterpret_cast<float4*>(o + it * ostep) = x;
+        if (row_first + 4 * it < M) {
+          *reinterpret_cast<float4*>(o + it * ostep) = x;
+          if constexpr (LN_OUT) {
+            uint2 pk;
+            pk.x = pack_bf16x2(x.x, x.y);
+            pk.y = pack_bf16x2(x.z, x.w);
+            *reinterpret_cast<uint2*>(ob + it * bstep) = pk;
+            st_s[it] += (x.x + x.y) + (x.z + x.w);
+            st_q[it] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+          }
+        }
       }
     } else {
       long orow[8];
@@ -161,6 +256,36 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
           }
         }
       }
+    }
+  }
+  if constexpr (LN_OUT) {
+    // The 8 lanes that share sub_row hold partial sums of the same 8 rows (16 columns each).  Recursive halving: every
+    // exchange sends half of the values still held and adds the half received (8 + 4 + 2 = 14 shuffles instead of a
+    // 48-shuffle butterfly); lane (b2 b1 b0) ends up with the totals of row `it` = 4*b2 + 2*b1 + b0 and adds them.
+    float v[16];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { v[2 * it] = st_s[it]; v[2 * it + 1] = st_q[it]; }
+    const bool b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+    float w8[8], w4[4], w2[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = b2 ? v[i] : v[i + 8];
+      w8[i] = (b2 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = b1 ? w8[i] : w8[i + 4];
+      w4[i] = (b1 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = b0 ? w4[i] : w4[i + 2];
+      w2[i] = (b0 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const int row = row_base + sub_row + 4 * (lane & 7);
+    if (row < M) {
+      atomicAdd(&ep.stats_out[row].x, w2[0]);
+      atomicAdd(&ep.stats_out[row].y, w2[1]);
     }
   }
 }

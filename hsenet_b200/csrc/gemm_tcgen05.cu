@@ -140,14 +140,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t stage = smem_epi + ew * EPI_WARP_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int tile_step = gridDim.x;
+    auto next_m0 = [&](int t) { return (t / n_tiles) * BM; };
+    float2 ln_sq[8];
+    if (static_cast<int>(blockIdx.x) < total_tiles)
+      epilogue_ln_load<MODE>(ep, next_m0(blockIdx.x) + quarter * 32, M, lane, ln_sq);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
+      float ln_a[8], ln_b[8];
+      epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
+      if (tile + tile_step < total_tiles)
+        epilogue_ln_load<MODE>(ep, next_m0(tile + tile_step) + quarter * 32, M, lane, ln_sq);
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       uint64_t* empty_bar = &bars->tmem_empty[acc];
       epilogue_slab<MODE>(ep, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_half * 128, stage,
-                    m0 + quarter * 32, n0 + col_half * 128, M, N, lane, [&]() {
+                    m0 + quarter * 32, n0 + col_half * 128, M, N, lane, ln_a, ln_b, [&]() {
                       // all TMEM reads of this accumulator stage by this warp are done: hand it back to the MMA warp
                       tc_fence_before();
                       __syncwarp();
@@ -191,6 +200,9 @@ int gemm_bf16_1cta(const void* A, int lda, const void* W, int ldw, int M, int N,
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_F32_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_BF16_GELU_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_kernel<EPI_F32_RESID_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     if (!ok) return HS_ERR_CUDA;
   }
   const int tiles = (N / BN) * ((M + BM - 1) / BM);
@@ -200,6 +212,9 @@ int gemm_bf16_1cta(const void* A, int lda, const void* W, int ldw, int M, int N,
     case EPI_BF16: launch_pdl(gemm_bf16_kernel<EPI_BF16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
     case EPI_BF16_GELU: launch_pdl(gemm_bf16_kernel<EPI_BF16_GELU>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
     case EPI_F32_RESID: launch_pdl(gemm_bf16_kernel<EPI_F32_RESID>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16_LN: launch_pdl(gemm_bf16_kernel<EPI_BF16_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16_GELU_LN: launch_pdl(gemm_bf16_kernel<EPI_BF16_GELU_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_F32_RESID_LN: launch_pdl(gemm_bf16_kernel<EPI_F32_RESID_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
     default: launch_pdl(gemm_bf16_kernel<EPI_GENERIC>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
   }
   count_launch();

@@ -204,14 +204,22 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t stage = smem_epi + ew * EPI_WARP_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int tile_step = num_pairs;
+    auto next_m0 = [&](int t) { return (t / n_tiles) * PM + static_cast<int>(cta_rank) * 128; };
+    float2 ln_sq[8];
+    if (pair < total_tiles) epilogue_ln_load<MODE>(ep, next_m0(pair) + quarter * 32, M, lane, ln_sq);
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       const int m0 = (tile / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
       const int n0 = (tile % n_tiles) * PN;
+      float ln_a[8], ln_b[8];
+      epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
+      if (tile + tile_step < total_tiles)
+        epilogue_ln_load<MODE>(ep, next_m0(tile + tile_step) + quarter * 32, M, lane, ln_sq);
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       uint64_t* empty_bar = &bars->tmem_empty[acc];
       epilogue_slab<MODE>(ep, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * PN + col_half * 128, stage,
-                    m0 + quarter * 32, n0 + col_half * 128, M, N, lane, [&]() {
+                    m0 + quarter * 32, n0 + col_half * 128, M, N, lane, ln_a, ln_b, [&]() {
                       tc_fence_before();
                       __syncwarp();
                       if (lane == 0) mbar_arrive_cluster(empty_bar, 0);   // the leader's MMA thread waits on it
@@ -251,6 +259,9 @@ int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N,
     ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_BF16_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_F32_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_BF16_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_BF16_GELU_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_F32_RESID_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     if (!ok) return HS_ERR_CUDA;
   }
   const int tiles = (N / PN) * ((M + PM - 1) / PM);
@@ -262,6 +273,9 @@ int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N,
     case EPI_BF16: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
     case EPI_BF16_GELU: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
     case EPI_F32_RESID: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16_GELU_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_F32_RESID_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
     default: launch_pdl(gemm_bf16_2cta_kernel<EPI_GENERIC>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
   }
   count_launch();

@@ -35,6 +35,12 @@ struct GemmEpilogue {
   int rows_per_group = 0;
   int group_stride = 0;
   int group_offset = 0;
+  // LayerNorm folded into the GEMMs on either side of it (gemm_epilogue.cuh):
+  float2* stats_out = nullptr;        // producer (EPI_F32_RESID): += (sum, sum of squares) of every output row
+  const float2* stats_in = nullptr;   // consumer (EPI_BF16[_GELU]): row statistics of the un-normalised A operand
+  const float* colsum = nullptr;      // consumer: sum_k W'[n,k] of the gain-folded weight
+  float ln_inv_dim = 0.f;             // 1 / (row length the statistics were taken over)
+  float ln_eps = 0.f;
 };
 
 // RAII CUDA-event bracket around one launch, active only between hsenet_profile_start/stop.
@@ -93,6 +99,8 @@ template <typename OutT>
 int im2col_patches(const float* vol, int B, OutT* out, cudaStream_t stream);
 template <typename OutT>
 int cast_rows(const float* in, OutT* out, long n, cudaStream_t stream);
+int fold_layernorm(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
+                   __nv_bfloat16* w_folded, float* colsum, float* bias_folded, cudaStream_t stream);
 int write_cls_rows(float* X, const float* cls, int B, int seq, cudaStream_t stream);
 // gather arbitrary-strided [B, rows, 768] (fp32 / bf16 / fp16 tagged by dtype code) into contiguous Act rows
 template <typename OutT>

@@ -505,6 +505,45 @@ int cast_rows(const float* in, OutT* out, long n, cudaStream_t stream) {
 template int cast_rows<float>(const float*, float*, long, cudaStream_t);
 template int cast_rows<__nv_bfloat16>(const float*, __nv_bfloat16*, long, cudaStream_t);
 
+// LayerNorm folded into the next linear layer (gemm_epilogue.cuh): one block per output feature n
+//   w_folded[n,k] = bf16(gamma[k] * w[n,k]);  colsum[n] = sum_k float(w_folded[n,k]);  bias_folded[n] = bias[n] + w[n,:] . beta
+namespace {
+__global__ void fold_layernorm_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                      __nv_bfloat16* __restrict__ wf, float* __restrict__ colsum,
+                                      float* __restrict__ bias_f, int K) {
+  __shared__ float red[2][8];
+  const long n = blockIdx.x;
+  float s = 0.f, bb = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = w[n * K + k];
+    const __nv_bfloat16 f = __float2bfloat16(wv * gamma[k]);
+    wf[n * K + k] = f;
+    s += __bfloat162float(f);          // the sum of what the tensor cores will actually multiply by
+    bb = fmaf(wv, beta[k], bb);
+  }
+  s = warp_sum(s);
+  bb = warp_sum(bb);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = bb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tb = 0.f;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) { ts += red[0][i]; tb += red[1][i]; }
+    colsum[n] = ts;
+    bias_f[n] = tb + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+}  // namespace
+
+int fold_layernorm(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
+                   __nv_bfloat16* w_folded, float* colsum, float* bias_folded, cudaStream_t stream) {
+  if (N <= 0 || K <= 0) return HS_OK;
+  fold_layernorm_kernel<<<static_cast<unsigned>(N), 256, 0, stream>>>(w, gamma, beta, bias, w_folded, colsum,
+                                                                      bias_folded, K);
+  count_launch();
+  return launch_status();
+}
+
 int write_cls_rows(float* X, const float* cls, int B, int seq, cudaStream_t stream) {
   if (B <= 0) return HS_OK;
   cls_rows_kernel<<<B, 192, 0, stream>>>(X, cls, seq);

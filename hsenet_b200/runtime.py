@@ -122,6 +122,24 @@ def _sig(params) -> tuple:
     return tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params)
 
 
+def fold_layernorm(norm, linear):
+    """(w_folded bf16 [N,K], colsum f32 [N], bias_folded f32 [N]) of ``linear(norm(x))`` -- hsenet_fold_layernorm."""
+    from . import _lib
+    w = f32(linear.weight)
+    n, k = w.shape
+    dev = w.device
+    wf = torch.empty(n, k, dtype=torch.bfloat16, device=dev)
+    cs = torch.empty(n, dtype=torch.float32, device=dev)
+    bf = torch.empty(n, dtype=torch.float32, device=dev)
+    bias = None if linear.bias is None else f32(linear.bias)
+    g, b = f32(norm.weight), f32(norm.bias)
+    with torch.cuda.device(dev):
+        rc = _lib.load().hsenet_fold_layernorm(w.data_ptr(), g.data_ptr(), b.data_ptr(), ptr(bias), n, k,
+                                               wf.data_ptr(), cs.data_ptr(), bf.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "fold_layernorm")
+    return wf, cs, bf
+
+
 def cast_weight(w: torch.Tensor, prec: str) -> torch.Tensor:
     """Matrix operand in the act dtype ([out,in] row-major, exactly as nn.Linear stores it)."""
     w = w.detach()

@@ -62,6 +62,17 @@ typedef struct hsenet_block_weights {
   const float* ln1_b;
   const float* ln2_g;  /* norm2 */
   const float* ln2_b;
+  /* Optional (bf16 precision only; leave NULL to run every LayerNorm as its own kernel): norm1 / norm2 folded into the
+   * linear layer that follows them, as produced by hsenet_fold_layernorm from the fp32 parameters.  With these set,
+   * norm2 of every block and norm1 of blocks >= 1 cost no kernel and no extra pass over the residual stream: the GEMM
+   * that writes the residual also writes its bf16 copy and per-row (sum, sum of squares), and the qkv / linear1 GEMM
+   * applies LN(x) W^T = rstd (x W'^T) - rstd mean colsum(W') + (W beta + b) in its epilogue. */
+  const void* w_qkv_ln;   /* bf16 [2304,768]  gamma1 (.) attn.qkv.weight      */
+  const float* cs_qkv;    /* [2304]           row sums of w_qkv_ln            */
+  const float* b_qkv_ln;  /* [2304]           attn.qkv.weight . beta1         */
+  const void* w_fc1_ln;   /* bf16 [3072,768]  gamma2 (.) mlp.linear1.weight   */
+  const float* cs_fc1;    /* [3072]                                            */
+  const float* b_fc1_ln;  /* [3072]           mlp.linear1.bias + weight . beta2 */
 } hsenet_block_weights;
 
 /* ViT_stage1 (vit.py:360-469) when stage == 1, ViT_stage2 (vit.py:222-357) when stage == 2. */
@@ -186,6 +197,10 @@ int hsenet_patch_gather_map(int32_t* out /*[2048,1024]*/, hsenet_stream_t stream
 int hsenet_packer_window_map(int32_t* out /*[128,16]*/, hsenet_stream_t stream);
 /* fp32 -> bf16 (round-to-nearest-even) cast used to build the weight cache. */
 int hsenet_cast_bf16(const float* in, void* out, long n, hsenet_stream_t stream);
+/* LayerNorm(gamma, beta) folded into the nn.Linear(w [N,K], bias [N] or NULL) that consumes it (weight cache):
+ * w_folded[n,k] = bf16(gamma[k] w[n,k]), colsum[n] = sum_k w_folded[n,k], bias_folded[n] = bias[n] + sum_k w[n,k] beta[k]. */
+int hsenet_fold_layernorm(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
+                          void* w_folded_bf16, float* colsum, float* bias_folded, hsenet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,38 @@ def test_vit_stage1(cuda, layers, B):
         assert torch.equal(m.last_patch_tokens, got[:, 1:])
 
 
+def test_layernorm_folded_into_gemms_matches_separate_kernels(cuda):
+    """bf16 path: norm1 / norm2 folded into the GEMM epilogues (default) against the same tower with every LayerNorm
+    as its own kernel, and both against the oracle.  LayerNorm gains / biases are randomised (util.randomize_params)
+    and given a large common offset here so that mean subtraction and the beta term are really exercised."""
+    import hsenet_b200 as H
+    m = _build(H.ViT_stage1, 3)
+    with torch.no_grad():
+        for blk in m.blocks:
+            blk.norm1.bias.add_(0.3)
+            blk.norm2.weight.mul_(1.7)
+    sd = cpu_state(m)
+    x, _ = synthetic_inputs(2)
+    ref, ref_h = O.vit_stage1(sd, x)
+    m = m.to(cuda)
+    m.return_hidden_states = True
+    m.use_cuda_graph = False            # direct launches: the kernel counter then counts exactly one forward
+    outs = {}
+    with torch.no_grad(), H.precision("bf16"):
+        for fold in (True, False):
+            m.fold_layernorm = fold
+            m(x.to(cuda))                   # builds the weight cache (the fold kernels run here)
+            n0 = H.runtime.kernel_launch_count()
+            got, hs = m(x.to(cuda))
+            outs[fold] = (got.float().cpu(), hs[-1].float().cpu(), H.runtime.kernel_launch_count() - n0)
+            print("fold", fold, assert_bf16(got, ref, f"vit_stage1 bf16 fold={fold}"))
+            assert_bf16(hs[-1], ref_h[-1], f"hidden[-1] bf16 fold={fold}")
+    mm = metrics(outs[True][0], outs[False][0])
+    assert mm["cos"] > 0.9999 and mm["max_rel"] < 1e-2, mm
+    # 3 blocks: norm2 of each + norm1 of blocks 1, 2 lose their kernel (5 launches), one memset is not a kernel
+    assert outs[False][2] - outs[True][2] == 5, (outs[True][2], outs[False][2])
+
+
 @pytest.mark.parametrize("layers,B", [(2, 2), (12, 1)])
 def test_vit_stage2(cuda, layers, B):
     import hsenet_b200 as H

@@ -199,6 +199,24 @@ def test_layernorm(lib, cuda):
     assert metrics(o16, ref)["max_rel"] < 5e-3
 
 
+def test_fold_layernorm(lib, cuda):
+    from hsenet_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    N, K = 2304, 768
+    W = torch.randn(N, K, generator=g) * 0.05
+    gm, bt, bias = 1 + 0.2 * torch.randn(K, generator=g), 0.3 * torch.randn(K, generator=g), torch.randn(N, generator=g)
+    Wd, gd, bd, biasd = W.to(cuda), gm.to(cuda), bt.to(cuda), bias.to(cuda)
+    wf = torch.empty(N, K, dtype=torch.bfloat16, device=cuda)
+    cs, bf = torch.empty(N, device=cuda), torch.empty(N, device=cuda)
+    for bptr, bref in ((biasd.data_ptr(), bias), (None, torch.zeros(N))):
+        _lib.check(lib.hsenet_fold_layernorm(Wd.data_ptr(), gd.data_ptr(), bd.data_ptr(), bptr, N, K, wf.data_ptr(),
+                                             cs.data_ptr(), bf.data_ptr(), _st()), "fold")
+        want = (W * gm).to(torch.bfloat16)
+        assert torch.equal(wf.cpu(), want)                                   # bit-exact rounding of gamma (.) W
+        assert metrics(cs, want.float().sum(1))["max_rel"] < 1e-5
+        assert metrics(bf, bref + W @ bt)["max_rel"] < 1e-5
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_packer_pool_and_window_attention(lib, cuda, dtype):
     from hsenet_b200 import _lib

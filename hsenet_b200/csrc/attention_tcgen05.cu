@@ -86,25 +86,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// ---- packed fp32x2 helpers (sm_100 FFMA2 / FADD2: two fp32 lanes per issued instruction) -------------------------
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 // 2^y for two values on the FMA / ALU pipes (no MUFU): y = n + f with n = round(y), f in [-0.5, 0.5]; cubic for 2^f
 // (relative error < 7e-4, inside bf16's 2^-9 rounding); the exponent is patched in with integer adds.  Used for a
 // fraction of the exponentials: the MUFU pipe (16 ex2/clk/SM) is what bounds the softmax.

@@ -287,8 +287,11 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               cudaStream_t stream) {
   const char* e = std::getenv("HSENET_GEMM_1CTA");     // read per call so tests can flip it in-process
   const bool force_1cta = e != nullptr && e[0] == '1';
-  if (force_1cta || M <= 128 || (K % 128) != 0) return gemm_bf16_1cta(A, lda, W, ldw, M, N, K, ep, stream);
-  return gemm_bf16_2cta(A, lda, W, ldw, M, N, K, ep, stream);
+  GemmEpilogue ep2 = ep;
+  const char* g = std::getenv("HSENET_GELU_ERF");      // 1: A&S exact-erf form also for bf16 outputs (A/B switch)
+  if (ep2.gelu != 0 && g != nullptr && g[0] == '1') ep2.gelu = 2;
+  if (force_1cta || M <= 128 || (K % 128) != 0) return gemm_bf16_1cta(A, lda, W, ldw, M, N, K, ep2, stream);
+  return gemm_bf16_2cta(A, lda, W, ldw, M, N, K, ep2, stream);
 }
 
 }  // namespace hs

@@ -75,6 +75,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Bounded spin that only traps (no printf call, so no call-clobbered state): for register-starved roles
+// (setmaxnreg.dec'ed issuer warps) and for code that keeps many registers live across the wait.
+__device__ __forceinline__ void mbar_wait_nocall(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // Same, with a nanosleep back-off between polls: for single-thread producer / issuer roles whose polling would
 // otherwise steal issue slots from the compute warps that share their SM sub-partition.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {

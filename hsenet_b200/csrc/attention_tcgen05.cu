@@ -9,18 +9,17 @@
 //     TMEM columns   0.. 63  S0      64..127  S1     128..159  P0     160..191  P1     192..255  O
 //   warp 0 lane 0  TMA producer: Q once, then K / V 128-key tiles straight out of the fused qkv activation
 //                  [B*S, 2304] (column offsets 0 / 768 / 1536 + h*64) -- no head-split copies are ever made;
-//   warp 1 lane 0  Q K^T issuer: S[b] = Q K^T (SS, both K-major, N = 64) for step t as soon as step t-2 has pulled its
-//                  scores into registers (s_free) and P V (t-2) has retired (pv_done) -- two steps ahead of the softmax;
-//   warp 0 lane 1  P V issuer: O += P[b] V (TS: P from TMEM, V is the MN-major B operand straight from its row-major
-//                  tile) as soon as P[b] is stored (p_full);
+//   warp 1 lane 0, warp 0 lane 1   MMA issuers of the even / odd steps: woken by p_full(t) a thread issues
+//                  O += P[b] V (TS: P from TMEM, V is the MN-major B operand straight from its row-major tile) and then
+//                  S[b] = Q K^T of step t+2 (SS, both K-major, N = 64), so that s_full(t+2) also certifies P[b] is free;
 //   warps 2..5     single-pass online softmax in fp32 (exp2 domain, lazy rescale): ONE mbarrier wait per step
-//                  (s_full, which also certifies that P[b] is free), 64 scores per thread in registers; O correction
-//                  only when the running max moved by more than 2^8; final normalise + bf16 store.
-// Why this shape (measured on B200: tools/umma_latency.cu, tools/ldtm_bw.cu, profiles/README.md): an mbarrier hop
-// costs ~250-300 cycles even when the phase is already complete and each tcgen05.mma issue 50-100 cycles on a busy SM,
-// while the exponentials of a 128x64 step need only 512 MUFU cycles per warp.  Earlier versions (single score buffer
-// and/or one issuing thread) serialised softmax and MMA chain and plateaued at ~195 us per layer for 8 volumes; here
-// both chains run two steps ahead of the softmax warps, which never wait on the tensor pipe.
+//                  (s_full), 64 scores per thread in registers; O correction only when the running max moved by more
+//                  than 2^8; final normalise + bf16 store.
+// Why this shape (measured on B200: tools/umma_latency.cu, umma_throughput.cu, attn_trace.py, profiles/README.md): a
+// barrier hop costs 200-400 cycles even when the phase is already complete, four tcgen05.mma issues + commit ~440 cycles
+// of the issuing thread on a loaded SM, and the step time is the cycle softmax(t) -> issuer -> softmax(t+2).  Splitting
+// the issuing work by MMA group (Q K^T thread / P V thread) put four hops on that cycle, a single issuing thread was
+// itself the bottleneck (~1200 busy cycles per step); splitting by step parity has two hops and half the work per thread.
 // Keys past the end of the sequence (2049 = 32*64 + 1) are masked in the last step; softmax warps whose 32 query rows
 // are all past the end (last query tile) skip the exponentials.
 #include "common.cuh"
@@ -52,7 +51,7 @@ struct AttBarriers {
   uint64_t q_full;
   uint64_t k_full[K_STAGES], k_empty[K_STAGES];
   uint64_t v_full[V_STAGES], v_empty[V_STAGES];
-  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
+  uint64_t s_full[2], p_full[2], pv_done[2];
   uint32_t tmem_base;
 };
 
@@ -131,11 +130,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(&bars->q_full, 1);
-    for (int s = 0; s < K_STAGES; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1); }
-    for (int s = 0; s < V_STAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
+    for (int s = 0; s < K_STAGES; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 2); }   // one commit per issuer
+    for (int s = 0; s < V_STAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 2); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->s_free[i], 4);
       mbar_init(&bars->p_full[i], 4);
       mbar_init(&bars->pv_done[i], 1);
     }
@@ -150,6 +148,57 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   pdl_prologue_done();      // everything above is independent of the previous kernel's output
+
+  // ===================== MMA issuer of the steps t = par, par+2, ... (two threads: par = 0, 1) =====================
+  // Woken by p_full(t), a thread issues P V (t) and then Q K^T (t+2) back to back.  Splitting the issuing work by step
+  // parity instead of by MMA group keeps two barrier hops on the cycle softmax(t) -> ... -> softmax(t+2) (a Q K^T / P V
+  // role split has four: p_full, pv_done -> Q K^T issuer, s_full; profiles/README.md) while each thread is busy only
+  // every other step (one thread for everything is itself the bottleneck at ~1200 busy cycles per step).  p_full(t)
+  // implies that softmax(t) holds S[par] in registers (no s_free barrier), and since one thread's MMAs complete in order
+  // s_full(t+2) implies that P V (t) has consumed P[par].  K / V stages are released by one commit from EACH thread.
+  auto mma_issuer = [&](const int par) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
+    constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);    // O[128q x 64d] += P V (V MN-major)
+    const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
+    auto issue_qk = [&](const int t) {                                    // k_full of its tile already waited for
+      const int ks = (t >> 1) % K_STAGES;
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + par * SUB_BYTES));
+#pragma unroll
+      for (int k = 0; k < kHeadDim / 16; ++k)
+        umma_ss(tmem_base + COL_S + par * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+      tc_commit(&bars->s_full[par]);
+      tc_commit(&bars->k_empty[ks]);
+    };
+    if (par >= nsub) return;
+    mbar_wait(&bars->q_full, 0);
+    mbar_wait(&bars->k_full[0], 0);
+    issue_qk(par);
+    ATT_TR_DECL;
+    for (int t = par; t < nsub; t += 2) {
+      const int j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
+      // operands of this iteration's MMAs first: long satisfied, kept off the critical path
+      mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+      if (t2 < nsub) mbar_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+      if (t == 1) mbar_wait(&bars->pv_done[0], 0);         // P V (0) initialises O: it must be in the pipe first
+      ATT_TR(0);
+      mbar_wait(&bars->p_full[par], (t >> 1) & 1);          // softmax t done: P[par] stored, S[par] in registers
+      tc_fence_after();
+      ATT_TR(1);
+      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
+#pragma unroll
+      for (int k = 0; k < KS / 16; ++k) {
+        // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes = +128 (16-byte units)
+        umma_ts(tmem_base + COL_O, tmem_base + COL_P + par * 32 + 8 * k, vdesc + 128 * k, idesc_pv,
+                (t | k) != 0 ? 1u : 0u);
+      }
+      tc_commit(&bars->pv_done[par]);
+      tc_commit(&bars->v_empty[vs]);
+      ATT_TR(2);
+      if (t2 < nsub) issue_qk(t2);
+      ATT_TR(3);
+    }
+    ATT_TR_DUMP(16 + 16 * par);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -168,59 +217,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
                          row0 + j * KT, kEvictLast);
       }
     } else if (lane == 1) {
-      // ===================== P V issuer =====================
-      constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);    // O[128q x 64d] += P V (V MN-major)
-      ATT_TR_DECL;
-      for (int t = 0; t < nsub; ++t) {
-        const int bsel = t & 1, j = t >> 1, vs = j % V_STAGES;
-        if (bsel == 0) mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
-        ATT_TR(0);
-        mbar_wait(&bars->p_full[bsel], (t >> 1) & 1);       // softmax t done: P[bsel] stored, O rescaled if needed
-        tc_fence_after();
-        ATT_TR(1);
-        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + bsel * SUB_BYTES));
-#pragma unroll
-        for (int k = 0; k < KS / 16; ++k) {
-          // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes = +128 (16-byte units)
-          umma_ts(tmem_base + COL_O, tmem_base + COL_P + bsel * 32 + 8 * k, vdesc + 128 * k, idesc_pv,
-                  (t | k) != 0 ? 1u : 0u);
-        }
-        ATT_TR(2);
-        tc_commit(&bars->pv_done[bsel]);
-        if (bsel == 1 || t == nsub - 1) tc_commit(&bars->v_empty[vs]);      // V tile fully consumed
-        ATT_TR(3);
-      }
-      ATT_TR_DUMP(32);
+      mma_issuer(1);
     }
   } else if (warp == 1) {
-    // ===================== Q K^T issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
-      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
-      mbar_wait(&bars->q_full, 0);
-      ATT_TR_DECL;
-      for (int t = 0; t < nsub; ++t) {
-        const int bsel = t & 1, j = t >> 1, ks = j % K_STAGES;
-        if (bsel == 0) mbar_wait(&bars->k_full[ks], (j / K_STAGES) & 1);
-        ATT_TR(0);
-        if (t >= 2) {
-          const uint32_t par = ((t >> 1) - 1) & 1;
-          mbar_wait(&bars->s_free[bsel], par);     // step t-2 holds its scores in registers: S[bsel] may be overwritten
-          mbar_wait(&bars->pv_done[bsel], par);    // P V (t-2) retired: P[bsel] may be overwritten by step t
-        }
-        tc_fence_after();
-        ATT_TR(1);
-        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + bsel * SUB_BYTES));
-#pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ss(tmem_base + COL_S + bsel * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        ATT_TR(2);
-        tc_commit(&bars->s_full[bsel]);
-        if (bsel == 1 || t == nsub - 1) tc_commit(&bars->k_empty[ks]);      // K tile fully consumed
-        ATT_TR(3);
-      }
-      ATT_TR_DUMP(16);
-    }
+    if (lane == 0) mma_issuer(0);
   } else {
     // ===================== softmax / correction / epilogue warps =====================
     const int quarter = warp & 3;
@@ -248,10 +248,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         tmem_ld_wait();
       }
       ATT_TR(1);
-      // the scores are in registers: the Q K^T issuer may refill S[bsel] (for step t+2) while we exponentiate
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_free[bsel]);
       ATT_TR(2);
       if (warp_live) {
         const int kbase = t * KS;
@@ -304,6 +300,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       // O correction (rare after the first steps): P V (t-1) must have retired before O is rescaled
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         mbar_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
+        if (t >= 2) mbar_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);   // the other issuing thread's P V (t-2)
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll 1

@@ -21,8 +21,7 @@ from hsenet_b200 import _lib  # noqa: E402
 PHASES = ["wait s_full + fence::after", "tcgen05.ld x2 + wait::ld", "fence + arrive s_free",
           "row max + lazy-rescale test", "exp2 / sum / pack", "tcgen05.st P (issue)", "O-correction vote (+rare path)",
           "wait::st + fence + arrive p_full"]
-QK = ["wait k_full", "wait s_free(t-2) + fence", "4 x tcgen05.mma issue", "commits"]
-PV = ["wait v_full", "wait p_full(t) + fence", "4 x tcgen05.mma issue", "commits"]
+ISSUER = ["operand waits (v_full, k_full)", "wait p_full(t) + fence", "4 x P V mma + 2 commits", "4 x Q K^T mma + 2 commits"]
 
 
 def main():
@@ -46,7 +45,7 @@ def main():
     torch.cuda.synchronize()
     buf = (C.c_ulonglong * 48)()
     assert fn(buf) == 0
-    for title, base, names in (("softmax warp 2", 0, PHASES), ("Q K^T issuer", 16, QK), ("P V issuer", 32, PV)):
+    for title, base, names in (("softmax warp 2", 0, PHASES), ("MMA issuer, even steps", 16, ISSUER), ("MMA issuer, odd steps", 32, ISSUER)):
         n = buf[base + 15]
         print(f"B={B} S={S} {title}: {n} steps, loop {buf[base + 14]} cycles = {buf[base + 14] / n:.0f} per step")
         for i, name in enumerate(names):

@@ -137,8 +137,6 @@ struct Prec<float> {
   }
 };
 
-inline bool ln_fold_disabled() { return false; }   // folding is selected by the caller: it supplies the folded weights
-
 template <typename T>
 inline void set_act_out(GemmEpilogue& ep, T* p, int ld) {
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p);
@@ -247,11 +245,11 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
   constexpr bool kCanFold = std::is_same<T, __nv_bfloat16>::value;
   auto folds_ln1 = [&](int l) {
     return kCanFold && l >= 1 && l < w->num_layers && l < kMaxFusedLayers && w->blocks_host[l].w_qkv_ln != nullptr &&
-           w->blocks_host[l].cs_qkv != nullptr && w->blocks_host[l].b_qkv_ln != nullptr && !ln_fold_disabled();
+           w->blocks_host[l].cs_qkv != nullptr && w->blocks_host[l].b_qkv_ln != nullptr;   // selected by the caller
   };
   auto folds_ln2 = [&](int l) {
     return kCanFold && l < kMaxFusedLayers && w->blocks_host[l].w_fc1_ln != nullptr &&
-           w->blocks_host[l].cs_fc1 != nullptr && w->blocks_host[l].b_fc1_ln != nullptr && !ln_fold_disabled();
+           w->blocks_host[l].cs_fc1 != nullptr && w->blocks_host[l].b_fc1_ln != nullptr;
   };
   bool any_fold = false;
   for (int l = 0; l < w->num_layers; ++l) any_fold |= folds_ln1(l) || folds_ln2(l);

@@ -234,6 +234,33 @@ def test_tower_config_variants(cuda, remain, select):
     assert tower.hidden_size == 768 and tower.device.type == "cuda"
 
 
+def test_concurrent_towers_match_serial_execution(cuda):
+    """The dual tower runs its two encoders on two streams (own workspaces, joined before returning): results must be
+    bit-identical to running them one after the other, also when the caller itself is on a non-default stream and
+    consumes the features right away."""
+    import hsenet_b200 as H
+    torch.manual_seed(0)
+    enc = randomize_params(H.HSENetVisualEncoder(H.VisionConfig())).eval().requires_grad_(False).to(cuda)
+    tower = enc.vision_tower
+    x, s = synthetic_inputs(2, seed=5)
+    x, s = x.to(cuda), s.to(cuda)
+    with torch.no_grad(), H.precision("bf16"):
+        tower.concurrent_towers = False
+        a1, a2 = tower(x, s)
+        tower.concurrent_towers = True
+        b1, b2 = tower(x, s)
+        assert torch.equal(a1, b1) and torch.equal(a2, b2)
+        side = torch.cuda.Stream(device=cuda)
+        side.wait_stream(torch.cuda.current_stream(cuda))
+        with torch.cuda.stream(side):
+            for _ in range(3):                      # back-to-back calls reuse the graphs' static buffers
+                c1, c2 = tower(x * 1.0, s)
+                tot = c1.float().sum() + c2.float().sum()
+        torch.cuda.current_stream(cuda).wait_stream(side)
+        assert torch.equal(c1, a1) and torch.equal(c2, a2)
+        assert torch.isfinite(tot)
+
+
 def test_input_dtypes_layouts_and_output_dtype(cuda):
     """Inputs arrive as fp32 in the reference even in bf16 runs, but fp16 / bf16 / non-contiguous tensors must work too
     (SURVEY 8b 'Threading / devices'); output_dtype controls the returned dtype."""

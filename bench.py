@@ -305,6 +305,7 @@ def main():
             ev_done = [torch.cuda.Event() for _ in range(2)]
             ev_out = [torch.cuda.Event() for _ in range(2)]
             host_out = [None, None]
+            live_out = [None, None]
             used = [False, False]
 
             def e2e_step(i):
@@ -322,12 +323,17 @@ def main():
                 outs = o if isinstance(o, tuple) else (o,)
                 if host_out[slot] is None:
                     host_out[slot] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+                if used[slot]:
+                    # The device tensors of step i-2 are released below.  No record_stream(): a block that another
+                    # stream has touched cannot be recycled until cross-stream events are polled complete, and the
+                    # caching allocator then falls back to a synchronising cudaMalloc every few steps (this made the
+                    # end-to-end number swing between 280 and 750 volumes/s).  Instead the compute stream waits for the
+                    # copy that read them, after which freeing them in stream order is safe.
+                    cur.wait_event(ev_out[slot])
+                live_out[slot] = outs
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(ev_done[slot])
-                    if used[slot]:
-                        pass                                      # host buffers are reused in order on one stream
-                    for hbuf, t in zip(host_out[slot], outs):
-                        t.record_stream(s_d2h)
+                    for hbuf, t in zip(host_out[slot], outs):      # host buffers are reused in order on one stream
                         hbuf.copy_(t, non_blocking=True)
                     ev_out[slot].record(s_d2h)
                 used[slot] = True

@@ -155,7 +155,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   // role split has four: p_full, pv_done -> Q K^T issuer, s_full; profiles/README.md) while each thread is busy only
   // every other step (one thread for everything is itself the bottleneck at ~1200 busy cycles per step).  p_full(t)
   // implies that softmax(t) holds S[par] in registers (no s_free barrier), and since one thread's MMAs complete in order
-  // s_full(t+2) implies that P V (t) has consumed P[par].  K / V stages are released by one commit from EACH thread.
+  // s_full(t+2) implies that P V (t) has consumed P[par].  K / V stages are released by one commit from EACH thread, and
+  // the P V groups of the two threads are kept in step order (deterministic accumulation into O).
   auto mma_issuer = [&](const int par) {
     constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
     constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);    // O[128q x 64d] += P V (V MN-major)
@@ -179,7 +180,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       // operands of this iteration's MMAs first: long satisfied, kept off the critical path
       mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
       if (t2 < nsub) mbar_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
-      if (t == 1) mbar_wait(&bars->pv_done[0], 0);         // P V (0) initialises O: it must be in the pipe first
+      // P V (t-1), issued by the other thread, must have retired before P V (t) is issued: both accumulate into the same
+      // fp32 tile, and an occasional swap of two accumulations would make the last bits differ from run to run (and
+      // P V (0) initialises O).  It retires long before p_full(t) arrives, so this wait is off the critical path too.
+      if (t >= 1) mbar_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);
       ATT_TR(0);
       mbar_wait(&bars->p_full[par], (t >> 1) & 1);          // softmax t done: P[par] stored, S[par] in registers
       tc_fence_after();

@@ -154,3 +154,53 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_dual_tower_two_stream_path_plumbing(monkeypatch):
+    """Host logic of ViT3DTower_dual_encoders._forward_concurrent with the CUDA side stubbed out: tower 1 is launched
+    inside the side-stream context, tower 2 on the caller's stream, both are finished (cloned) only after the join, and
+    .train() mode of the 2E3 encoder is still rejected on this path."""
+    import contextlib
+    import hsenet_b200 as H
+    from hsenet_b200 import vit
+    tw = H.ViT3DTower_dual_encoders(H.VisionConfig()).eval()
+    log = []
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name = name
+
+        def wait_stream(self, other):
+            log.append(("wait", self.name, other.name))
+
+    cur, side = FakeStream("cur"), FakeStream("side")
+    active = ["cur"]
+
+    @contextlib.contextmanager
+    def fake_stream_ctx(s):
+        active.append(s.name)
+        try:
+            yield
+        finally:
+            active.pop()
+
+    monkeypatch.setattr(vit.rt, "side_stream", lambda dev: side)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: cur)
+    monkeypatch.setattr(torch.cuda, "stream", fake_stream_ctx)
+    for t in (tw.vision_tower_stage1, tw.vision_tower_stage2):
+        def launch(x, s, _t=t):
+            log.append(("launch", _t._stage, active[-1], s is not None))
+            return (torch.zeros(1, 2049, 768), torch.zeros(1, 2048, 768), None, None), True, torch.float32
+
+        def finish(launched, _t=t, _orig=t._finish):
+            log.append(("finish", _t._stage, active[-1]))
+            return _orig(launched)
+        monkeypatch.setattr(t, "_launch", launch)
+        monkeypatch.setattr(t, "_finish", finish)
+    f1, f2 = tw._forward_concurrent(torch.zeros(1, 1, 32, 256, 256), torch.zeros(1, 32, 768))
+    assert f1.shape == f2.shape == (1, 2048, 768)
+    assert log == [("wait", "side", "cur"), ("launch", 1, "side", False), ("launch", 2, "cur", True),
+                   ("wait", "cur", "side"), ("finish", 1, "cur"), ("finish", 2, "cur")]
+    tw.vision_tower_stage2.train()
+    with pytest.raises(NotImplementedError):
+        tw._forward_concurrent(torch.zeros(1, 1, 32, 256, 256), torch.zeros(1, 32, 768))

@@ -20,12 +20,13 @@ from .lamed_arch import (HSENetVisualEncoder, VisionConfig, encode_images, encod
 from .dist_utils import gather_features
 from .clip import ClipImageHead, clip_image_head, contrastive_logits
 from .slices import extract_slices
+from .preprocess import preprocess_ct_volume
 
 __all__ = [
     "ViT_stage1", "ViT_stage2", "ViT3DTower_dual_encoders", "regular_attention",
     "VisualPacker_3d_phi_v3", "resolution_attention_v3", "build_vision_tower", "build_mm_projector",
     "encode_images", "encode_images_with", "prepare_inputs_for_multimodal", "splice_visual_tokens",
     "HSENetVisualEncoder", "VisionConfig", "gather_features",
-    "ClipImageHead", "clip_image_head", "contrastive_logits", "extract_slices",
+    "ClipImageHead", "clip_image_head", "contrastive_logits", "extract_slices", "preprocess_ct_volume",
     "set_precision", "get_precision", "precision", "release_workspaces",
 ]

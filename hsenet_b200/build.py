@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libhsenet_sm100a.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention_tcgen05.cu", "rowops.cu", "verify_fp32.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention_tcgen05.cu", "rowops.cu", "ingest.cu", "verify_fp32.cu"]
 HEADERS = ["common.cuh", "kernels.h", "gemm_epilogue.cuh", os.path.join("..", "..", "include", "hsenet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

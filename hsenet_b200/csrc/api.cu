@@ -622,5 +622,25 @@ int hsenet_fold_layernorm(const float* w, const float* gamma, const float* beta,
   return fold_layernorm(w, gamma, beta, bias, N, K, static_cast<__nv_bfloat16*>(w_folded_bf16), colsum, bias_folded,
                         static_cast<cudaStream_t>(stream));
 }
+int hsenet_hu_resample(const float* raw, int n0, int n1, int n2, float slope, float intercept, float hu_min,
+                       float hu_max, float* out, int o0, int o1, int o2, hsenet_stream_t stream) {
+  if (raw == nullptr || out == nullptr) return HSENET_ERR_ARG;
+  return hu_resample(raw, n0, n1, n2, slope, intercept, hu_min, hu_max, out, o0, o1, o2,
+                     static_cast<cudaStream_t>(stream));
+}
+int hsenet_minmax(const float* x, long n, float* minmax2, int32_t* scratch2, hsenet_stream_t stream) {
+  if (x == nullptr || minmax2 == nullptr || scratch2 == nullptr) return HSENET_ERR_ARG;
+  return minmax(x, n, minmax2, scratch2, static_cast<cudaStream_t>(stream));
+}
+int hsenet_foreground_bbox(const float* x, int d0, int d1, int d2, const float* minmax2, int32_t* bbox6,
+                           hsenet_stream_t stream) {
+  if (x == nullptr || minmax2 == nullptr || bbox6 == nullptr) return HSENET_ERR_ARG;
+  return foreground_bbox(x, d0, d1, d2, minmax2, bbox6, static_cast<cudaStream_t>(stream));
+}
+int hsenet_crop_normalize_resize(const float* x, int d0, int d1, int d2, const float* minmax2, const int32_t* bbox6,
+                                 float* out, int o0, int o1, int o2, hsenet_stream_t stream) {
+  if (x == nullptr || minmax2 == nullptr || bbox6 == nullptr || out == nullptr) return HSENET_ERR_ARG;
+  return crop_normalize_resize(x, d0, d1, d2, minmax2, bbox6, out, o0, o1, o2, static_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

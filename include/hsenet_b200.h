@@ -197,6 +197,22 @@ int hsenet_patch_gather_map(int32_t* out /*[2048,1024]*/, hsenet_stream_t stream
 int hsenet_packer_window_map(int32_t* out /*[128,16]*/, hsenet_stream_t stream);
 /* fp32 -> bf16 (round-to-nearest-even) cast used to build the weight cache. */
 int hsenet_cast_bf16(const float* in, void* out, long n, hsenet_stream_t stream);
+/* ---- volume ingest: Data/data_processing/CT-RATE/CT-RATE_nii_to_3D_volume_npy_file.py:25-117.
+ * All four calls are asynchronous on `stream`; min / max and the foreground box stay in device memory, so the chain
+ * raw volume -> [32,256,256] network input needs no host synchronisation. */
+/* raw [n0,n1,n2] (NIfTI array order, slice index contiguous) -> out [o0,o1,o2] = trilinear(align_corners=False) resample
+ * of clamp(slope*raw + intercept, hu_min, hu_max) viewed as [n2,n0,n1]  (lines 25-38, 73-91) */
+int hsenet_hu_resample(const float* raw, int n0, int n1, int n2, float slope, float intercept, float hu_min,
+                       float hu_max, float* out, int o0, int o1, int o2, hsenet_stream_t stream);
+/* exact global min / max -> minmax2[0..1] (device); scratch2 = 2 ints of device scratch  (lines 103-104) */
+int hsenet_minmax(const float* x, long n, float* minmax2, int32_t* scratch2, hsenet_stream_t stream);
+/* MONAI CropForeground (select_fn x > 0 on the min-max normalised volume == x > min): bbox6 = lo0,lo1,lo2,hi0,hi1,hi2
+ * with hi exclusive (device); the full extent if nothing is foreground  (line 116) */
+int hsenet_foreground_bbox(const float* x, int d0, int d1, int d2, const float* minmax2, int32_t* bbox6,
+                           hsenet_stream_t stream);
+/* (x - min) / max(max - min, 1e-8) on the box, trilinear(align_corners=False) resize to [o0,o1,o2]  (lines 105-106, 117) */
+int hsenet_crop_normalize_resize(const float* x, int d0, int d1, int d2, const float* minmax2, const int32_t* bbox6,
+                                 float* out, int o0, int o1, int o2, hsenet_stream_t stream);
 /* LayerNorm(gamma, beta) folded into the nn.Linear(w [N,K], bias [N] or NULL) that consumes it (weight cache):
  * w_folded[n,k] = bf16(gamma[k] w[n,k]), colsum[n] = sum_k w_folded[n,k], bias_folded[n] = bias[n] + sum_k w[n,k] beta[k]. */
 int hsenet_fold_layernorm(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,

@@ -282,6 +282,53 @@ def slice_extract(images: torch.Tensor, out_hw=(224, 224)) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+# Volume ingest: Data/data_processing/CT-RATE/CT-RATE_nii_to_3D_volume_npy_file.py
+# PARITY UNPINNED against the script itself: MONAI's CropForeground / Resize sources are not in the reference tree (restated
+# here from their documented behaviour: select_fn x > 0, margin 0, Resize(mode='bilinear') == trilinear with
+# align_corners=False on a 3-D volume), the script resamples in float64, and it needs nibabel + the metadata CSV.
+# --------------------------------------------------------------------------------------------------
+def preprocess_resampled_shape(raw_shape, xy_spacing, z_spacing, target=(1.5, 0.75, 0.75)):
+    """new_shape of resize_array (script lines 30-35) for the (2,0,1)-transposed volume."""
+    n0, n1, n2 = raw_shape
+    cur = (z_spacing, xy_spacing, xy_spacing)
+    orig = (n2, n0, n1)
+    return tuple(int(orig[i] * (cur[i] / target[i])) for i in range(3))
+
+
+def foreground_bbox(x: torch.Tensor):
+    """MONAI generate_spatial_bounding_box(select_fn=is_positive, margin=0) on a [z,a,b] volume: (lo, hi) with hi exclusive;
+    the full extent when nothing is positive."""
+    fg = x > 0
+    if not bool(fg.any()):
+        return (0, 0, 0), tuple(x.shape)
+    lo, hi = [], []
+    for d in range(3):
+        other = tuple(i for i in range(3) if i != d)
+        idx = torch.nonzero(fg.any(dim=other)).reshape(-1)
+        lo.append(int(idx[0]))
+        hi.append(int(idx[-1]) + 1)
+    return tuple(lo), tuple(hi)
+
+
+def preprocess_volume(raw: torch.Tensor, slope, intercept, xy_spacing, z_spacing, out_size=(32, 256, 256),
+                      dtype=torch.float32, return_intermediates=False):
+    """nii_img_to_tensor + transform (script lines 41-117) on an in-memory voxel array raw [n0,n1,n2]."""
+    x = (slope * raw.to(dtype) + intercept).clamp(-1000, 200)                       # lines 80-86
+    x = x.permute(2, 0, 1)[None, None]                                              # lines 90, 93-94
+    new_shape = preprocess_resampled_shape(raw.shape, xy_spacing, z_spacing)
+    x = F.interpolate(x, size=new_shape, mode="trilinear", align_corners=False)[0, 0]   # lines 37, 97
+    x = x.float()                                                                   # line 102
+    mn, mx = x.min(), x.max()                                                       # lines 111-112
+    xn = (x - mn) / torch.clamp(mx - mn, min=1e-8)                                  # lines 113-114
+    lo, hi = foreground_bbox(xn)                                                    # CropForeground, line 122
+    crop = xn[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+    out = F.interpolate(crop[None, None], size=tuple(out_size), mode="trilinear", align_corners=False)[0]   # Resize
+    if return_intermediates:
+        return out, x, (float(mn), float(mx)), lo + hi
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # Parity metrics used by every test (north_star tolerances)
 # --------------------------------------------------------------------------------------------------
 def parity_metrics(got: torch.Tensor, ref: torch.Tensor) -> dict:

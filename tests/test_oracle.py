@@ -145,3 +145,21 @@ def test_gather_features_reference_single_process():
         assert torch.equal(ra, ga) and torch.equal(rb, gb)
     finally:
         dist.destroy_process_group()
+
+
+def test_ingest_oracle_restatement():
+    """Row f-4 (parity unpinned against the script, see oracle header): shapes, range, and the CropForeground box on a
+    volume whose air border survives an identity resample exactly."""
+    g = torch.Generator().manual_seed(9)
+    raw = torch.randint(-1200, 600, (96, 80, 40), generator=g).float()
+    raw[:8] = -2000; raw[-8:] = -2000; raw[:, :8] = -2000; raw[:, -8:] = -2000
+    out, res, (mn, mx), box = O.preprocess_volume(raw, 1.0, 0.0, 0.75, 1.5, return_intermediates=True)
+    assert out.shape == (1, 32, 256, 256) and res.shape == (40, 96, 80)
+    assert (mn, mx) == (-1000.0, 200.0) and box == (0, 8, 8, 40, 88, 72)
+    assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    assert O.preprocess_resampled_shape((512, 512, 303), 0.7, 1.0) == (int(303 * (1.0 / 1.5)), int(512 * (0.7 / 0.75)),
+                                                                      int(512 * (0.7 / 0.75)))
+    x = torch.zeros(5, 6, 7)
+    assert O.foreground_bbox(x) == ((0, 0, 0), (5, 6, 7))
+    x[1, 2, 3] = 1.0; x[3, 4, 6] = 2.0
+    assert O.foreground_bbox(x) == ((1, 2, 3), (4, 5, 7))

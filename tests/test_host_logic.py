@@ -204,3 +204,16 @@ def test_dual_tower_two_stream_path_plumbing(monkeypatch):
     tw.vision_tower_stage2.train()
     with pytest.raises(NotImplementedError):
         tw._forward_concurrent(torch.zeros(1, 1, 32, 256, 256), torch.zeros(1, 32, 768))
+
+
+def test_preprocess_host_logic():
+    """Row f-4 host side: the resampled shape follows the script's int(orig * cur / target) per axis of the transposed
+    volume (and agrees with the oracle), CPU tensors fail loudly, malformed inputs are rejected."""
+    import hsenet_b200 as H
+    from hsenet_b200 import preprocess as P
+    from util import O
+    for shape, xy, z in (((512, 512, 303), 0.7, 1.0), ((96, 80, 40), 0.9, 2.0), ((64, 64, 33), 0.75, 1.5)):
+        assert P.resampled_shape(shape, xy, z) == O.preprocess_resampled_shape(shape, xy, z)
+    assert P.resampled_shape((64, 64, 33), 0.75, 1.5) == (33, 64, 64)          # identity spacing: pure transpose
+    with pytest.raises(RuntimeError):
+        H.preprocess_ct_volume(torch.zeros(8, 8, 8), 1.0, 0.0, 0.75, 1.5)      # CPU tensor: no fallback

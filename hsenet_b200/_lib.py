@@ -65,7 +65,7 @@ SIGNATURES = {
     "hsenet_packer_window_map": (C.c_int, [vp, vp]),
     "hsenet_cast_bf16": (C.c_int, [vp, vp, C.c_long, vp]),
     "hsenet_hu_resample": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp,
-                                     C.c_int, C.c_int, C.c_int, vp]),
+                                     C.c_int, C.c_int, C.c_int, vp, vp]),
     "hsenet_minmax": (C.c_int, [vp, C.c_long, vp, vp, vp]),
     "hsenet_foreground_bbox": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "hsenet_crop_normalize_resize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),

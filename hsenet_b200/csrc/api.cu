@@ -623,9 +623,9 @@ int hsenet_fold_layernorm(const float* w, const float* gamma, const float* beta,
                         static_cast<cudaStream_t>(stream));
 }
 int hsenet_hu_resample(const float* raw, int n0, int n1, int n2, float slope, float intercept, float hu_min,
-                       float hu_max, float* out, int o0, int o1, int o2, hsenet_stream_t stream) {
+                       float hu_max, float* out, int o0, int o1, int o2, float* scratch, hsenet_stream_t stream) {
   if (raw == nullptr || out == nullptr) return HSENET_ERR_ARG;
-  return hu_resample(raw, n0, n1, n2, slope, intercept, hu_min, hu_max, out, o0, o1, o2,
+  return hu_resample(raw, n0, n1, n2, slope, intercept, hu_min, hu_max, out, o0, o1, o2, scratch,
                      static_cast<cudaStream_t>(stream));
 }
 int hsenet_minmax(const float* x, long n, float* minmax2, int32_t* scratch2, hsenet_stream_t stream) {

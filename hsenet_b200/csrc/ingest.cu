@@ -83,6 +83,45 @@ __global__ void __launch_bounds__(256) hu_resample_kernel(const float* __restric
   }
 }
 
+// Two-pass variant (used when the caller provides scratch of the raw size): windowed 32x32 tiled transpose
+// [n0*n1][n2] -> [n2][n0*n1], then a resample whose eight taps are b-contiguous across adjacent threads.
+__global__ void __launch_bounds__(256) hu_transpose_kernel(const float* __restrict__ raw, long rows, int cols,
+                                                           float slope, float intercept, float lo, float hi,
+                                                           float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const long r0 = static_cast<long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const long r = r0 + ty + k;
+    const int c = c0 + tx;
+    if (r < rows && c < cols) t[ty + k][tx] = fminf(fmaxf(slope * __ldg(raw + r * cols + c) + intercept, lo), hi);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int c = c0 + ty + k;
+    const long r = r0 + tx;
+    if (r < rows && c < cols) out[static_cast<long>(c) * rows + r] = t[tx][ty + k];
+  }
+}
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, int d0, int d1, int d2,
+                                                       float* __restrict__ out, int o0, int o1, int o2, float s0,
+                                                       float s1, float s2) {
+  const long total = static_cast<long>(o0) * o1 * o2;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i % o2);
+    const int a = static_cast<int>((i / o2) % o1);
+    const int z = static_cast<int>(i / (static_cast<long>(o2) * o1));
+    const Axis t = src_index(z, d0, s0), h = src_index(a, d1, s1), w = src_index(b, d2, s2);
+    out[i] = trilinear(t, h, w, [&](int zz, int aa, int bb) {
+      return __ldg(x + (static_cast<long>(zz) * d1 + aa) * d2 + bb);
+    });
+  }
+}
+
 // order-preserving float <-> int so that integer atomics give an exact float min / max
 __device__ __forceinline__ int f2ord(float f) {
   const int i = __float_as_int(f);
@@ -193,9 +232,19 @@ inline unsigned grid_for(long n) {
 }  // namespace
 
 int hu_resample(const float* raw, int n0, int n1, int n2, float slope, float intercept, float hu_min, float hu_max,
-                float* out, int o0, int o1, int o2, cudaStream_t st) {
+                float* out, int o0, int o1, int o2, float* scratch, cudaStream_t st) {
   if (n0 <= 0 || n1 <= 0 || n2 <= 0 || o0 <= 0 || o1 <= 0 || o2 <= 0) return HS_ERR_SHAPE;
   const float s0 = static_cast<float>(n2) / o0, s1 = static_cast<float>(n0) / o1, s2 = static_cast<float>(n1) / o2;
+  if (scratch != nullptr) {
+    const long rows = static_cast<long>(n0) * n1;
+    const dim3 tg(static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>((n2 + 31) / 32));
+    hu_transpose_kernel<<<tg, 256, 0, st>>>(raw, rows, n2, slope, intercept, hu_min, hu_max, scratch);
+    resample_kernel<<<grid_for(static_cast<long>(o0) * o1 * o2), 256, 0, st>>>(scratch, n2, n0, n1, out, o0, o1, o2,
+                                                                               s0, s1, s2);
+    count_launch();
+    count_launch();
+    return launch_ok();
+  }
   // staged sub-block per tile: (T*scale + 3) source indices per axis at most
   const long need = static_cast<long>(TA * s1 + 3) * static_cast<long>(TB * s2 + 3) * static_cast<long>(TZ * s0 + 3);
   if (need > kRawTileFloats) return HS_ERR_SHAPE;          // down-sampling by more than ~4x per axis: not an ingest case

@@ -101,7 +101,7 @@ template <typename OutT>
 int cast_rows(const float* in, OutT* out, long n, cudaStream_t stream);
 // volume ingest (ingest.cu)
 int hu_resample(const float* raw, int n0, int n1, int n2, float slope, float intercept, float hu_min, float hu_max,
-                float* out, int o0, int o1, int o2, cudaStream_t st);
+                float* out, int o0, int o1, int o2, float* scratch, cudaStream_t st);
 int minmax(const float* x, long n, float* minmax2, int* scratch2, cudaStream_t st);
 int foreground_bbox(const float* x, int d0, int d1, int d2, const float* minmax2, int* bbox6, cudaStream_t st);
 int crop_normalize_resize(const float* x, int d0, int d1, int d2, const float* minmax2, const int* bbox6, float* out,

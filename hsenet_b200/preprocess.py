@@ -28,7 +28,7 @@ def resampled_shape(raw_shape, xy_spacing: float, z_spacing: float):
 
 
 def preprocess_ct_volume(raw: torch.Tensor, slope: float, intercept: float, xy_spacing: float, z_spacing: float,
-                         out_size=OUT_SIZE, return_intermediates: bool = False):
+                         out_size=OUT_SIZE, return_intermediates: bool = False, two_pass: bool = True):
     """raw: CUDA fp32 ``[n0, n1, n2]`` in NIfTI array order (``nib.load(p).get_fdata()``).  Returns ``[1, *out_size]`` fp32."""
     rt.require_cuda(raw, "raw volume")
     if raw.dim() != 3:
@@ -46,9 +46,12 @@ def preprocess_ct_volume(raw: torch.Tensor, slope: float, intercept: float, xy_s
     scratch = torch.empty(2, dtype=torch.int32, device=dev)
     bbox = torch.empty(6, dtype=torch.int32, device=dev)
     out = torch.empty((1,) + tuple(out_size), dtype=torch.float32, device=dev)
+    # two_pass: windowed tiled transpose into a scratch volume, then a coalesced resample (faster); else one gather pass
+    tscratch = torch.empty_like(x) if two_pass else None
     with torch.cuda.device(dev):
         _lib.check(lib.hsenet_hu_resample(x.data_ptr(), n0, n1, n2, float(slope), float(intercept), HU_WINDOW[0],
-                                          HU_WINDOW[1], res.data_ptr(), o[0], o[1], o[2], st), "hu_resample")
+                                          HU_WINDOW[1], res.data_ptr(), o[0], o[1], o[2], rt.ptr(tscratch), st),
+                   "hu_resample")
         _lib.check(lib.hsenet_minmax(res.data_ptr(), res.numel(), mm.data_ptr(), scratch.data_ptr(), st), "minmax")
         _lib.check(lib.hsenet_foreground_bbox(res.data_ptr(), o[0], o[1], o[2], mm.data_ptr(), bbox.data_ptr(), st),
                    "foreground_bbox")

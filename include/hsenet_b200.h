@@ -201,9 +201,10 @@ int hsenet_cast_bf16(const float* in, void* out, long n, hsenet_stream_t stream)
  * All four calls are asynchronous on `stream`; min / max and the foreground box stay in device memory, so the chain
  * raw volume -> [32,256,256] network input needs no host synchronisation. */
 /* raw [n0,n1,n2] (NIfTI array order, slice index contiguous) -> out [o0,o1,o2] = trilinear(align_corners=False) resample
- * of clamp(slope*raw + intercept, hu_min, hu_max) viewed as [n2,n0,n1]  (lines 25-38, 73-91) */
+ * of clamp(slope*raw + intercept, hu_min, hu_max) viewed as [n2,n0,n1]  (lines 25-38, 73-91).
+ * scratch: n0*n1*n2 floats of device memory (windowed transpose, then a coalesced resample) or NULL (one gather pass). */
 int hsenet_hu_resample(const float* raw, int n0, int n1, int n2, float slope, float intercept, float hu_min,
-                       float hu_max, float* out, int o0, int o1, int o2, hsenet_stream_t stream);
+                       float hu_max, float* out, int o0, int o1, int o2, float* scratch, hsenet_stream_t stream);
 /* exact global min / max -> minmax2[0..1] (device); scratch2 = 2 ints of device scratch  (lines 103-104) */
 int hsenet_minmax(const float* x, long n, float* minmax2, int32_t* scratch2, hsenet_stream_t stream);
 /* MONAI CropForeground (select_fn x > 0 on the min-max normalised volume == x > min): bbox6 = lo0,lo1,lo2,hi0,hi1,hi2

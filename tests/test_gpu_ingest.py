@@ -26,6 +26,10 @@ def test_hu_resample_matches_interpolate(cuda, shape, xy, z):
     raw = _raw(shape, 1)
     slope, intercept = 1.0, -24.0
     out, res, mm, bbox = P.preprocess_ct_volume(raw.to(cuda), slope, intercept, xy, z, return_intermediates=True)
+    out1, res1, _, _ = P.preprocess_ct_volume(raw.to(cuda), slope, intercept, xy, z, return_intermediates=True,
+                                              two_pass=False)
+    # same arithmetic in both variants up to FMA contraction (values span +-1000)
+    assert (res - res1).abs().max() <= 1e-3 and (out - out1).abs().max() <= 1e-5
     x = (slope * raw + intercept).clamp(-1000, 200).permute(2, 0, 1)[None, None]
     ref = F.interpolate(x, size=P.resampled_shape(shape, xy, z), mode="trilinear", align_corners=False)[0, 0]
     assert res.shape == ref.shape == O.preprocess_resampled_shape(shape, xy, z)

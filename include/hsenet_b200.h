@@ -163,8 +163,8 @@ int hsenet_clip_image_head(const void* tokens, const void* w_proj, const float* 
 
 /* ---- operator-level entry points (unit-tested individually; the composites are built from these) ------------- */
 
-/* out = epilogue(A[M,K] * W[N,K]^T): bias, optional exact-erf GELU, optional fp32 residual (may alias out_f32),
- * fp32 and/or act outputs.  nn.Linear semantics (MONAI SABlock.qkv/out_proj, MLPBlock.linear1/2, ...). */
+/* out = epilogue(A[M,K] * W[N,K]^T): bias, optional GELU (the exact-erf function; bf16-only outputs evaluate a tanh form
+ * fitted to it, max |err| 2.5e-5, below bf16 rounding), optional fp32 residual (may alias out_f32), fp32 and/or act outputs.  nn.Linear semantics (MONAI SABlock.qkv/out_proj, MLPBlock.linear1/2, ...). */
 int hsenet_linear(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                   const float* resid, int ld_resid, int gelu, float* out_f32, int ld_f32, void* out_act,
                   int ld_act, int precision, hsenet_stream_t stream);

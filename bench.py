@@ -1,14 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- CT volumes/s of the HSENet visual-encoding hot path on B200 (see BASELINE.json / SURVEY.md section 8d).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--batch B] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one batch of synthetic volumes per GPU.
-  workload c2 (default, BASELINE.json configs[1]): dual encoder forward -- ViT_stage1 + ViT_stage2 (2E3) on the same
-      batch of 8 volumes per GPU, bf16.  1017.22 algorithmic GFLOP per volume.
-  workload c3 (configs[2]): dual encoder + the two spatial packers -> [B,256,3072], batch 32 per GPU. 1033.54 GFLOP/volume.
+  workload c3 (default, BASELINE.json configs[2] = the full north-star path, lamed_arch.py:122-141): dual encoder + the two
+      spatial packers -> [B,256,3072], batch 32 per GPU, bf16.  1033.54 algorithmic GFLOP per volume.
+  workload c2 (configs[1]): dual encoder forward only, batch 8 per GPU. 1017.22 GFLOP/volume.  Also measured (short) inside
+      the default run and reported under the extra key "c2".
+  workload c4 (configs[3]): stage-1 CLIP image side with the packed NCCL all-gather; at N > 1 the default run also reports
+      it under "clip_step" together with an in-bench check of the collective's result.
+Extra keys of the default line: "c2", "clip_step" (N > 1), "gpu_eager_baseline" (the reference algorithm as eager PyTorch
+under bf16 autocast on the same B200, N = 1), "roofline_attention" (tensor and MUFU bounds), "roofline_packer" and
+"roofline_layernorm" (HBM), "cpu_baseline".
 Prints ONE JSON line (rank 0).  `value` = volumes/s with inputs resident in HBM (CUDA events, max over ranks);
 `e2e` = the same through the public module API with pinned HOST inputs, H2D and D2H inside the timed region.
 `--impl reference` times the reference algorithm's CPU path (the oracle port, fp32 eager PyTorch, all host threads) on a
@@ -130,11 +136,12 @@ def run_step(enc, workload, x, s):
         if "head" not in _c4_state:
             torch.manual_seed(1)
             _c4_state["head"] = H.ClipImageHead().eval().requires_grad_(False).to(x.device)
-            g = torch.Generator().manual_seed(99)
+            g = torch.Generator().manual_seed(99 + int(os.environ.get("RANK", "0")))      # every rank its own captions
             _c4_state["text"] = torch.nn.functional.normalize(torch.randn(x.shape[0], 768, generator=g)).to(x.device)
             _c4_state["scale"] = torch.tensor(1.0 / 0.07, device=x.device)
         tokens, _ = enc.vision_tower.vision_tower_stage1(x)
         emb = _c4_state["head"](tokens)                                    # [B_loc,768] unit-norm, fp32
+        _c4_state["emb"] = emb
         _, lpi, _ = H.contrastive_logits(emb, _c4_state["text"], _c4_state["scale"])   # NCCL all-gather inside
         return lpi                                                          # [B_global, B_global]
     return enc(x, s)                                  # [B,256,3072]
@@ -170,16 +177,112 @@ def cpu_reference_run(workload, threads, reps):
     return times
 
 
+def _event_ms(fn, reps, dev):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_c2(enc, dev, rank, world, barrier, max_over_ranks, steps=10):
+    """BASELINE configs[1] (dual encoder forward, batch 8 per GPU) as a short extra measurement."""
+    B2 = DEFAULT_BATCH["c2"]
+    sets = [(x.to(dev), s.to(dev)) for x, s in make_inputs(B2, rank, 4, pinned=False)]
+    for i in range(3):
+        run_step(enc, "c2", *sets[i % 4])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        run_step(enc, "c2", *sets[i % 4])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    v = B2 * world * steps / (ms * 1e-3)
+    return {"workload": WORKLOAD_NAME["c2"], "value": v, "unit": "volumes/s", "volumes_per_gpu_per_step": B2,
+            "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
+            "step_tflops_per_gpu": v / world * GFLOP_PER_VOLUME["c2"] / 1e3}
+
+
+def measure_clip_step(enc, dev, rank, world, x, s, barrier, max_over_ranks, steps=5):
+    """BASELINE configs[3]: stage-1 ViT -> cls head -> gather_features (ONE packed NCCL all-gather) -> [B,B] logits, with the
+    all-gather timed on its own and its result checked on every rank against the reference formulation
+    (utils/dist_utils.py:292-293: rank-ordered concatenation of per-rank all_gather lists)."""
+    import torch.distributed as dist
+    import hsenet_b200 as H
+    B = x.shape[0]
+    for _ in range(2):
+        run_step(enc, "c4", x, s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        lpi = run_step(enc, "c4", x, s)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    emb, text = _c4_state["emb"], _c4_state["text"]
+    ag_ms = max_over_ranks(_event_ms(lambda: H.gather_features(emb, text), 20, dev))
+    all_i, all_t = H.gather_features(emb, text)
+    li = [torch.empty_like(emb) for _ in range(world)]
+    lt = [torch.empty_like(text) for _ in range(world)]
+    dist.all_gather(li, emb)
+    dist.all_gather(lt, text)
+    ok = (torch.equal(all_i, torch.cat(li, 0)) and torch.equal(all_t, torch.cat(lt, 0))
+          and torch.equal(all_i[rank * B:(rank + 1) * B], emb) and tuple(lpi.shape) == (B * world, B * world)
+          and bool(torch.isfinite(lpi).all()))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    v = B * world * steps / (ms * 1e-3)
+    return {"workload": WORKLOAD_NAME["c4"], "value": v, "unit": "volumes/s", "ranks": world,
+            "volumes_per_gpu_per_step": B, "global_batch": B * world, "steps": steps, "ms_per_step": ms / steps,
+            "all_gather_us": ag_ms * 1e3, "all_gather_bytes_per_rank": int(emb.numel() * 4 + text.numel() * 4),
+            "logits_shape": list(lpi.shape), "backend": dist.get_backend(),
+            "collective_check": "ok" if int(flag.item()) == 1 else "MISMATCH",
+            "check": "every rank: packed all_gather_into_tensor result == rank-ordered cat of dist.all_gather lists "
+                     "(bit-exact), own block == local embeddings, logits finite; MIN-reduced over ranks"}
+
+
+def gpu_eager_baseline(enc, dev, B=8, reps=3):
+    """The reference algorithm (oracle port of vit.py / packer, materialised scores, eager PyTorch kernels) on the SAME
+    B200 under bf16 autocast: BASELINE.md section 4's 'reference on the same box' number.  A baseline leg, like cpu_baseline."""
+    from oracle import hsenet_oracle as O
+    tsd = {k: v.detach().float() for k, v in enc.vision_tower.state_dict().items()}
+    p1 = {k: v.detach().float() for k, v in enc.mm_projector.state_dict().items()}
+    p2 = {k: v.detach().float() for k, v in enc.mm_projector2.state_dict().items()}
+    g = torch.Generator().manual_seed(4321)
+    x = torch.rand(B, 1, 32, 256, 256, generator=g).to(dev)
+    s = torch.randn(B, 32, 768, generator=g).to(dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return O.encode_images(tsd, p1, p2, x, s)
+
+    step()
+    ms = _event_ms(step, reps, dev)
+    del tsd, p1, p2
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms, "volumes_per_step": B, "steps": reps,
+            "kind": "port", "dtype": "bf16 autocast (fp32 softmax / LayerNorm)",
+            "how": "oracle port of the reference modules run as eager PyTorch (cuBLAS GEMMs, materialised "
+                   "[B,12,2049,2049] scores) on the same GPU, full C3 path"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4"])
     ap.add_argument("--batch", type=int, default=0, help="volumes per GPU per step (default: 8 for c2, 32 for c3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c2 / clip_step / gpu_eager_baseline records")
     args = ap.parse_args()
 
     # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner from C) write to fd 1 too, so
@@ -236,7 +339,7 @@ def main():
     lib = _lib.load()
     H.set_precision("bf16")
     enc = build_modules(args.workload, dev)
-    n_sets = 4                                            # 4 x 67 MB (B=8) of inputs > 126 MB L2: inputs come from HBM
+    n_sets = 4 if B <= 8 else 2                           # >= 268 MB of rotating inputs > 126 MB L2: inputs come from HBM
     host_sets = make_inputs(B, rank, n_sets, pinned=True)
     dev_sets = [(x.to(dev), s.to(dev)) for x, s in host_sets]
     config["l2_policy"] = (f"{n_sets} rotating input sets ({n_sets * B * 8.39:.0f} MB) + ~{B * 0.28:.1f} GB of "
@@ -285,7 +388,8 @@ def main():
         lib.hsenet_profile_start()
         for i in range(K):
             run_step(enc, args.workload, *dev_sets[i % n_sets])
-        ms = (C.c_double * 4)(); fl = (C.c_double * 4)(); by = (C.c_double * 4)(); ln = (C.c_uint64 * 4)()
+        NC = _lib.PROFILE_CLASSES
+        ms = (C.c_double * NC)(); fl = (C.c_double * NC)(); by = (C.c_double * NC)(); ln = (C.c_uint64 * NC)()
         _lib.check(lib.hsenet_profile_stop(ms, fl, by, ln), "profile_stop")
         for tw in (enc.vision_tower.vision_tower_stage1, enc.vision_tower.vision_tower_stage2):
             tw.use_cuda_graph = True
@@ -357,6 +461,18 @@ def main():
                    "how": "public module API, pinned host inputs/outputs, H2D and D2H of every step inside the timed "
                           "region on side streams (double buffered) overlapping the previous/next step's compute"}
 
+        # ---- extra records (short): C2, the C4 CLIP step with its collective (N > 1), eager PyTorch on the same GPU (N = 1)
+        extras = {}
+        if not args.no_extras and args.workload == "c3":
+            extras["c2"] = measure_c2(enc, dev, rank, world, barrier, max_over_ranks)
+            if world > 1:
+                extras["clip_step"] = measure_clip_step(enc, dev, rank, world, *dev_sets[0], barrier, max_over_ranks)
+            elif rank == 0:
+                try:
+                    extras["gpu_eager_baseline"] = gpu_eager_baseline(enc, dev)
+                except Exception as exc:                       # a baseline leg must never take the bench line down
+                    extras["gpu_eager_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,29 +491,67 @@ def main():
             traffic = json.load(open(tp)).get("gemm_bf16_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+
+    def hbm_record(cls, kernel):
+        gbs = by[cls] / (ms[cls] * 1e-3) / 1e9 if ms[cls] > 0 else 0.0
+        return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "launches": int(ln[cls]),
+                "avg_launch_us": ms[cls] / ln[cls] * 1e3 if ln[cls] else None,
+                "algorithmic_mb_per_launch": by[cls] / ln[cls] / 1e6 if ln[cls] else None}
+
+    # attention: d = 64 makes the exponentials, not the MMAs, the longer pole: 4*64 = 256 tensor FLOPs per score against
+    # one ex2, i.e. 32 tensor-pipe cycles vs 64 MUFU cycles per 128x64 tile row at 8192 FLOP/clk and 16 ex2/clk per SM
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    mufu_peak = 16.0 * 148 * sm_max * 1e6                       # ex2 per second per GPU at the maximum SM clock
+    att_exps = fl[1] / (4.0 * 64)                               # one exponential per score
+    att_exp_rate = att_exps / (ms[1] * 1e-3) if ms[1] > 0 else 0.0
+    att_bounds = {
+        "tensor": {"achieved": att_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                   "frac": att_tf / peaks["bf16_sustained"]},
+        "mufu": {"achieved": att_exp_rate / 1e12, "peak": mufu_peak / 1e12, "unit": "Tex2/s",
+                 "frac": att_exp_rate / mufu_peak,
+                 "note": "algorithmic exponentials (one per score) against 16 ex2/clk/SM x 148 SMs at the maximum SM clock; "
+                         "the kernel evaluates 2 of every 8 on the FMA pipe instead"},
+    }
     line = {
         "metric": "CT volumes/s encoded", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": {
-            "kernel": "gemm_bf16_kernel (tcgen05; 69% of the path's FLOPs)", "bound": "tensor",
+            "kernel": "gemm_bf16_2cta_kernel (tcgen05 cta_group::2; 69% of the path's FLOPs)", "bound": "tensor",
             "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": gemm_tf / peaks["bf16_sustained"], "traffic": traffic,
+            "frac_of_burst_peak": gemm_tf / peaks["bf16_burst"],
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
             "launches": int(ln[0]), "avg_launch_ms": ms[0] / ln[0] if ln[0] else None,
             "how": "algorithmic 2*M*N*K per launch / CUDA-event duration per launch, instrumented re-run of the same steps",
         },
-        "roofline_attention": {"kernel": "attention_kernel (tcgen05 flash attention; 31% of FLOPs)", "bound": "tensor",
+        "roofline_attention": {"kernel": "attention_split_kernel (tcgen05 flash attention; 31% of FLOPs)",
+                               "bound": "mufu" if att_bounds["mufu"]["frac"] > att_bounds["tensor"]["frac"] else "tensor",
                                "achieved": att_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                               "frac": att_tf / peaks["bf16_sustained"], "launches": int(ln[1])},
-        "roofline_layernorm": {"kernel": "layernorm_kernel", "bound": "hbm", "achieved": ln_gbs,
-                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ln_gbs / peaks["hbm_gbs"],
-                               "launches": int(ln[2])},
+                               "frac": att_tf / peaks["bf16_sustained"], "bounds": att_bounds, "launches": int(ln[1]),
+                               "avg_launch_us": ms[1] / ln[1] * 1e3 if ln[1] else None},
+        "roofline_layernorm": hbm_record(2, "layernorm_kernel"),
         "roofline_step": {"achieved": step_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                          "frac": step_tf / peaks["bf16_sustained"], "gflop_per_volume": gflop,
-                          "share_ms": {"gemm": ms[0] / K, "attention": ms[1] / K, "layernorm": ms[2] / K}},
+                          "frac": step_tf / peaks["bf16_sustained"], "frac_of_burst_peak": step_tf / peaks["bf16_burst"],
+                          "gflop_per_volume": gflop,
+                          "share_ms": {"gemm": ms[0] / K, "attention": ms[1] / K, "layernorm": ms[2] / K,
+                                       "packer_pool": ms[4] / K, "packer_window_attn": ms[5] / K, "im2col": ms[6] / K,
+                                       "slice_xattn": ms[7] / K, "score_scale": ms[8] / K}},
     }
+    if ln[4] or ln[5]:
+        pk_ms, pk_by = ms[4] + ms[5], by[4] + by[5]
+        gbs = pk_by / (pk_ms * 1e-3) / 1e9 if pk_ms > 0 else 0.0
+        line["roofline_packer"] = {
+            "kernel": "packer_pool_kernel + packer_window_attn_kernel", "bound": "hbm", "achieved": gbs,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "pool": hbm_record(4, "packer_pool_kernel"), "window_attention": hbm_record(5, "packer_window_attn_kernel"),
+            "algorithmic_bytes": "pool: 2048x768 in + 128x768 out (bf16) per volume; window attention: 2048x1536 bf16 K|V "
+                                 "+ 128x768 fp32 Q + 128x768 bf16 out per volume"}
+    line["roofline_rowops"] = {"im2col": hbm_record(6, "im2col_kernel"), "slice_xattn": hbm_record(7, "slice_xattn_kernel"),
+                               "score_scale": hbm_record(8, "score_scale_kernel")}
+    line.update(extras)
     if e2e is not None:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -15,6 +15,7 @@ OK = 0
 ERR_SHAPE, ERR_ALIGN, ERR_CUDA, ERR_ARG, ERR_DRIVER = -1, -2, -3, -4, -5
 PREC_BF16, PREC_FP32_VERIFY = 0, 1
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+PROFILE_CLASSES = 10      # HSENET_PROFILE_CLASSES
 
 vp = C.c_void_p
 

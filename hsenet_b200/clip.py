@@ -41,11 +41,11 @@ def clip_image_head(tokens: torch.Tensor, proj: nn.Linear, cache: rt.WeightCache
     if t.dtype != act or not t.is_contiguous():
         t = t.to(act).contiguous()
     build = lambda p: {"w": rt.cast_weight(proj.weight, p), "b": rt.f32(proj.bias)}
-    pl = cache.get(proj.parameters(), prec, build) if cache is not None else build(prec)
     B = t.shape[0]
     out = torch.empty(B, 768, dtype=torch.float32, device=t.device)
     ws = rt.workspace(t.device, B * 768 * 4, "clip_head")
     with torch.cuda.device(t.device):
+        pl = cache.get(proj.parameters(), prec, build) if cache is not None else build(prec)
         rc = _lib.load().hsenet_clip_image_head(t.data_ptr(), pl["w"].data_ptr(), pl["b"].data_ptr(), B,
                                                 rt.precision_code(prec), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 rt.stream_ptr(t.device))

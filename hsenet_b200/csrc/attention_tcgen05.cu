@@ -360,6 +360,258 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   }
 }
 
+
+// =====================================================================================================================
+// Key-split variant (default since round 2): EIGHT softmax warps per CTA, two per TMEM lane quarter.  The two warps of a
+// quarter share the same 32 query rows and split every 64-key step by KEY half (keys 0..31 / 32..63): each keeps its own
+// running max, row sum and its OWN fp32 output accumulator (O_A / O_B in TMEM, fed by the K = 32 halves of P V), so no
+// row statistic is ever exchanged inside the loop -- the two partial softmaxes are merged once, in the epilogue
+// (m* = max(m_A, m_B); O = (O_A 2^(m_A-m*) + O_B 2^(m_B-m*)) / (l_A 2^(m_A-m*) + l_B 2^(m_B-m*))).
+// Why: the round-1 kernel was a per-warp LATENCY chain (mbarrier probe ~230 cycles, tcgen05.ld, max, 64 exponentials,
+// tcgen05.st + wait ~400, arrive) with one softmax warp per scheduler and CTA -- a CTA ran as fast alone on an SM as with
+// a partner and no unit was above 50 % (profiles/README.md).  Eight warps halve the serial exp/max work per warp-step
+// and put four independent chains on every scheduler (2 CTAs x 2 warps), without the shared-memory max exchange that
+// made the row-sharing v3/v9 slower.  P is aliased onto the first half of its own score columns (a warp overwrites only
+// columns it has already read into registers; Q K^T (t+2) is issued after P V (t) by the same thread, so the MMA pipe
+// orders the overwrite), which keeps the CTA at 256 TMEM columns and two CTAs per SM:
+//     TMEM columns   0.. 63  S0 (P0_A at 0..15, P0_B at 32..47)    64..127  S1 (P1_A, P1_B)    128..191 O_A    192..255 O_B
+// Issuing threads, TMA rings and the step-parity protocol are those of the kernel above; p_full counts 8 warps.
+constexpr int ATS_THREADS = 320;
+constexpr uint32_t ATS_COL_S = 0, ATS_COL_O = 128;
+constexpr int ATS_SMEM = ATT_SMEM + 2 * 128 * 8;
+
+template <int POLY>
+__global__ void __launch_bounds__(ATS_THREADS, 2)
+attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = sK + K_STAGES * TILE_BYTES;
+  AttBarriers* bars = reinterpret_cast<AttBarriers*>(sV + V_STAGES * TILE_BYTES);
+  float2* ml = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 halves][128 rows] (m, l)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row0 = b * S;
+  const int ntiles = (S + KT - 1) / KT;
+  const int nsub = (S + KS - 1) / KS;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < K_STAGES; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 2); }
+    for (int s = 0; s < V_STAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 2); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 8);
+      mbar_init(&bars->pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  pdl_prologue_done();
+
+  auto mma_issuer = [&](const int par) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);
+    const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
+    auto issue_qk = [&](const int t) {
+      const int ks = (t >> 1) % K_STAGES;
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + par * SUB_BYTES));
+#pragma unroll
+      for (int k = 0; k < kHeadDim / 16; ++k)
+        umma_ss(tmem_base + ATS_COL_S + par * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+      tc_commit(&bars->s_full[par]);
+      tc_commit(&bars->k_empty[ks]);
+    };
+    if (par >= nsub) return;
+    mbar_wait(&bars->q_full, 0);
+    mbar_wait(&bars->k_full[0], 0);
+    issue_qk(par);
+    for (int t = par; t < nsub; t += 2) {
+      const int j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
+      mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+      if (t2 < nsub) mbar_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+      if (t >= 1) mbar_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);   // keep the accumulation order fixed
+      mbar_wait(&bars->p_full[par], (t >> 1) & 1);
+      tc_fence_after();
+      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
+#pragma unroll
+      for (int k = 0; k < KS / 16; ++k) {
+        // key half k>>1: A = 16 keys = 8 packed columns at the start of that half's score columns, D = that half's O
+        const int half = k >> 1;
+        umma_ts(tmem_base + ATS_COL_O + half * kHeadDim, tmem_base + ATS_COL_S + par * KS + half * 32 + 8 * (k & 1),
+                vdesc + 128 * k, idesc_pv, (t | (k & 1)) != 0 ? 1u : 0u);
+      }
+      tc_commit(&bars->pv_done[par]);
+      tc_commit(&bars->v_empty[vs]);
+      if (t2 < nsub) issue_qk(t2);
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tmQKV, &bars->q_full, h * kHeadDim, row0 + q0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int ks = j % K_STAGES, vs = j % V_STAGES;
+        mbar_wait(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->k_full[ks], TILE_BYTES);
+        tma_load_2d_hint(sK + ks * TILE_BYTES, &tmQKV, &bars->k_full[ks], kHidden + h * kHeadDim, row0 + j * KT,
+                         kEvictLast);
+        mbar_wait(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
+        tma_load_2d_hint(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * kHidden + h * kHeadDim,
+                         row0 + j * KT, kEvictLast);
+      }
+    } else if (lane == 1) {
+      mma_issuer(1);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) mma_issuer(0);
+  } else {
+    // ===================== softmax warps: quarter = TMEM lane quarter (warp % 4), half = key half =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const int qi = q0 + quarter * 32 + lane;
+    const bool warp_live = (q0 + quarter * 32) < S;
+    const float c = 0.125f * 1.4426950408889634f;
+    const uint32_t col_o = ATS_COL_O + half * kHeadDim;
+    float m = -INFINITY;
+    float l = 0.f;
+    auto softmax_step = [&](const int t, auto masked) {
+      const int bsel = t & 1;
+      const uint32_t col_s = ATS_COL_S + bsel * KS + half * 32;
+      mbar_wait(&bars->s_full[bsel], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t x[32];
+      uint32_t pk[16];
+      float alpha = 1.f;
+      if (warp_live) {
+        tmem_ld32(tmem_base + lane_base + col_s, x);
+        tmem_ld_wait();
+        if constexpr (decltype(masked)::value) {
+          const int kbase = t * KS + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + i >= S) x[i] = 0xff800000u;
+        }
+        float mx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx[u] = __uint_as_float(x[u]);
+#pragma unroll
+        for (int i = 4; i < 32; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(x[i + u]));
+        }
+        const float tm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
+        if (tm > m + 8.0f) {
+          alpha = ex2(m - tm);
+          m = tm;
+        }
+        // a half that has not seen a valid key yet (only possible in a masked step) keeps m = -inf: subtract 0 instead,
+        // so that the all -inf scores give exp2(-inf) = 0 and not exp2(-inf + inf)
+        float msub = m;
+        if constexpr (decltype(masked)::value) msub = (m == -INFINITY) ? 0.f : m;
+        const uint64_t c2 = pack2(c, c), nm2 = pack2(-msub, -msub);
+        uint64_t rs2 = pack2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float e[8];
+#pragma unroll
+          for (int u = 0; u < 8; u += 2)
+            unpack2(fma2(pack2(__uint_as_float(x[i + u]), __uint_as_float(x[i + u + 1])), c2, nm2), e[u], e[u + 1]);
+#pragma unroll
+          for (int u = 0; u < 8 - POLY; ++u) e[u] = ex2(e[u]);
+#pragma unroll
+          for (int u = 8 - POLY; u < 8; u += 2) exp2_poly2(e[u], e[u + 1], e[u], e[u + 1]);
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            rs2 = add2(rs2, pack2(e[u], e[u + 1]));
+            pk[(i + u) >> 1] = pack_bf16x2(e[u], e[u + 1]);
+          }
+        }
+        float rs0, rs1;
+        unpack2(rs2, rs0, rs1);
+        l = l * alpha + (rs0 + rs1);
+        tmem_st16(tmem_base + lane_base + col_s, pk);
+      }
+      if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
+        if (t >= 2) mbar_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
+        tc_fence_after();
+        uint32_t o[32];
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          tmem_ld32(tmem_base + lane_base + col_o + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_base + lane_base + col_o + ch * 32, o);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
+    };
+    const bool ragged = (S % KS) != 0;
+    for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
+    if (ragged) softmax_step(nsub - 1, std::true_type{});
+    // ---- merge the two key halves and store: this warp takes output columns [half*32, half*32+32) of its 32 rows ----
+    ml[half * 128 + quarter * 32 + lane] = make_float2(m, l);
+    asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 softmax warps only
+    const float2 other = ml[(half ^ 1) * 128 + quarter * 32 + lane];
+    const float ms = fmaxf(m, other.x);
+    const float w_self = ex2(m - ms), w_other = ex2(other.x - ms);
+    const float inv = 1.0f / (l * w_self + other.y * w_other);
+    const float fa = (half == 0 ? w_self : w_other) * inv;          // weight of O_A
+    const float fb = (half == 0 ? w_other : w_self) * inv;          // weight of O_B
+    if (nsub >= 2) mbar_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
+    mbar_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
+    tc_fence_after();
+    uint32_t oa[32], ob[32];
+    tmem_ld32(tmem_base + lane_base + ATS_COL_O + half * 32, oa);
+    tmem_ld32(tmem_base + lane_base + ATS_COL_O + kHeadDim + half * 32, ob);
+    tmem_ld_wait();
+    if (qi < S) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long>(row0) + qi) * kHidden + h * kHeadDim + half * 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = __uint_as_float(oa[g * 8 + u]) * fa + __uint_as_float(ob[g * 8 + u]) * fb;
+        uint4 u4;
+        u4.x = pack_bf16x2(v[0], v[1]);
+        u4.y = pack_bf16x2(v[2], v[3]);
+        u4.z = pack_bf16x2(v[4], v[5]);
+        u4.w = pack_bf16x2(v[6], v[7]);
+        dst[g] = u4;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, cudaStream_t stream) {
@@ -374,16 +626,27 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
     ok &= cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_split_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM) == cudaSuccess;
     if (!ok) return HS_ERR_CUDA;
   }
   ProfScope prof(PROF_ATTENTION, 4.0 * B * kHeads * double(S) * S * kHeadDim, 2.0 * B * double(S) * 4 * kHidden,
                  stream);
   const char* e = std::getenv("HSENET_ATT_POLY");        // share of exponentials emulated on the FMA pipe (0 / 2 / 4 of 8)
   const int poly = e != nullptr ? std::atoi(e) : kDefaultPoly;
+  const char* kv = std::getenv("HSENET_ATT_KERNEL");     // "rowwarp" = the round-1 kernel (4 softmax warps), for A/B runs
+  const bool split = !(kv != nullptr && kv[0] == 'r');
   const dim3 grid((S + QT - 1) / QT, kHeads, B);
-  if (poly >= 4) launch_pdl(attention_kernel<4>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-  else if (poly >= 2) launch_pdl(attention_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-  else launch_pdl(attention_kernel<0>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+  if (split) {
+    if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
+    else if (poly >= 2) launch_pdl(attention_split_kernel<2>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
+    else launch_pdl(attention_split_kernel<0>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
+  } else {
+    if (poly >= 4) launch_pdl(attention_kernel<4>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    else if (poly >= 2) launch_pdl(attention_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    else launch_pdl(attention_kernel<0>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+  }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
 }

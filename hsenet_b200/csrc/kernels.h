@@ -44,7 +44,10 @@ struct GemmEpilogue {
 };
 
 // RAII CUDA-event bracket around one launch, active only between hsenet_profile_start/stop.
-enum : int { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_OTHER = 3 };
+enum : int {
+  PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_OTHER = 3, PROF_PACKER_POOL = 4, PROF_PACKER_WATTN = 5,
+  PROF_IM2COL = 6, PROF_SLICE_XATTN = 7, PROF_SCORE_SCALE = 8, PROF_SLICE_EXTRACT = 9,
+};
 struct ProfScope {
   ProfScope(int cls, double flops, double bytes, cudaStream_t st);
   ~ProfScope();

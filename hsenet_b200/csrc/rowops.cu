@@ -484,6 +484,7 @@ template <typename OutT>
 int im2col_patches(const float* vol, int B, OutT* out, cudaStream_t stream) {
   if (B <= 0) return HS_OK;
   if (!aligned16(vol) || !aligned16(out)) return HS_ERR_ALIGN;
+  ProfScope prof(PROF_IM2COL, 0.0, double(B) * kNPatch * kPatchDim * (4.0 + sizeof(OutT)), stream);
   im2col_kernel<OutT><<<B * 128, 256, 0, stream>>>(vol, out);
   count_launch();
   return launch_status();
@@ -591,6 +592,8 @@ int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn,
         cudaSuccess)
       return HS_ERR_CUDA;
   }
+  ProfScope prof(PROF_SLICE_XATTN, 4.0 * B * kNPatch * double(kNSlice) * kHidden,
+                 double(B) * (kNPatch * kHidden * (4.0 + sizeof(OutT)) + kNSlice * 2.0 * kHidden * 4.0), stream);
   slice_xattn_kernel<OutT><<<dim3(kNPatch / kXaRowsPerCta, B), 256, smem, stream>>>(Q, KV, O, attn);
   count_launch();
   return launch_status();
@@ -603,6 +606,7 @@ int score_and_scale(const float* Z, const float* ln_g, const float* ln_b, const 
                     const float* XP, float* X, float* scores, int B, cudaStream_t stream) {
   const long total = static_cast<long>(B) * kNPatch;
   if (total <= 0) return HS_OK;
+  ProfScope prof(PROF_SCORE_SCALE, 0.0, double(total) * kHidden * 12.0, stream);
   score_scale_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(Z, ln_g, ln_b, w_s, b_s, XP, X,
                                                                                  scores, total);
   count_launch();
@@ -613,6 +617,7 @@ template <typename T>
 int packer_pool(const T* HR, T* LR, int B, cudaStream_t stream) {
   const long total = static_cast<long>(B) * 128;
   if (total <= 0) return HS_OK;
+  ProfScope prof(PROF_PACKER_POOL, 0.0, double(B) * (kNPatch + 128.0) * kHidden * sizeof(T), stream);
   packer_pool_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(HR, LR, total);
   count_launch();
   return launch_status();
@@ -624,6 +629,8 @@ template <typename T>
 int packer_window_attention(const float* Q, const T* KV, T* O, int B, cudaStream_t stream) {
   const long total = static_cast<long>(B) * 128;
   if (total <= 0) return HS_OK;
+  ProfScope prof(PROF_PACKER_WATTN, 0.0,
+                 double(B) * (128.0 * kHidden * (4.0 + sizeof(T)) + kNPatch * 2.0 * kHidden * sizeof(T)), stream);
   packer_window_attn_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(Q, KV, O, total);
   count_launch();
   return launch_status();
@@ -646,6 +653,7 @@ int slice_extract(const float* vol, OutT* out, int B, int oh, int ow, cudaStream
   if (oh <= 0 || ow <= 0 || ow > 256 || oh > 65535 || (ow % 4)) return HS_ERR_SHAPE;
   const float sy = 256.0f / static_cast<float>(oh);
   const float sx = 256.0f / static_cast<float>(ow);
+  ProfScope prof(PROF_SLICE_EXTRACT, 0.0, double(B) * 32.0 * (256.0 * 256.0 * 4.0 + 3.0 * oh * ow * sizeof(OutT)), stream);
   slice_extract_kernel<OutT><<<dim3((oh + 3) / 4, B * 32), 256, 0, stream>>>(vol, out, oh, ow, sy, sx);
   count_launch();
   return launch_status();

@@ -46,13 +46,24 @@ class _PackedAllGather(torch.autograd.Function):
 
 
 def gather_features(image_features, text_features, local_loss=False, gather_with_grad=True, rank=0, world_size=1):
+    """Rank-ordered concatenation of every rank's image / text features (dist_utils.py:280-306).
+
+    ``rank`` / ``world_size`` are accepted for signature compatibility; like every reference call site (which passes
+    the process group's own values, CLIP_stage1.py:143) the exchange uses the initialised process group's rank and
+    size.  Each returned tensor keeps its input's dtype (mixed dtypes -- fp32 image features from the cls head with
+    bf16 text features under autocast -- travel as the wider one and are cast back)."""
     assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
     world, my_rank = _world()
     if world == 1:
         # the reference bootstraps a 1-process group and gathers a single block (train_CLIP_stage1.py:29-38)
         return image_features, text_features
+    if image_features.dim() != 2 or image_features.shape != text_features.shape:
+        raise ValueError(f"gather_features packs image and text features into one buffer: both must be [B_loc, D] of "
+                         f"the same shape, got {tuple(image_features.shape)} and {tuple(text_features.shape)}")
     b = image_features.shape[0]
-    packed = torch.stack([image_features, text_features], dim=1)          # [B_loc, 2, D]
+    dt_i, dt_t = image_features.dtype, text_features.dtype
+    wire = torch.promote_types(dt_i, dt_t)
+    packed = torch.stack([image_features.to(wire), text_features.to(wire)], dim=1)          # [B_loc, 2, D]
     if gather_with_grad:
         allp = _PackedAllGather.apply(packed)                             # [W, B_loc, 2, D]
     else:
@@ -63,4 +74,4 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
             allp = allp.clone()
             allp[my_rank] = packed
     allp = allp.reshape(world * b, 2, -1)
-    return allp[:, 0], allp[:, 1]
+    return allp[:, 0].to(dt_i), allp[:, 1].to(dt_t)

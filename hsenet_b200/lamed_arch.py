@@ -14,7 +14,11 @@ from .builder import build_mm_projector, build_vision_tower
 
 
 def encode_images_with(tower, mm_projector, mm_projector2, images, images_2d, out_dtype=None):
-    feats = tower(images, images_2d)
+    return pack_features(tower(images, images_2d), mm_projector, mm_projector2, out_dtype)
+
+
+def pack_features(feats, mm_projector, mm_projector2, out_dtype=None):
+    """Tower features -> LLM-space visual tokens (lamed_arch.py:125-139)."""
     if isinstance(feats, tuple):
         if feats[-1].shape[1] != 2048:
             raise ValueError("dual-tower encode_images expects select_feature == 'patch' (2048 tokens per tower), "
@@ -71,6 +75,18 @@ def splice_visual_tokens(tower, mm_projector, mm_projector2, inputs_embeds, imag
         raise ValueError(f"sequence of {L} tokens cannot hold {n1 + n2} visual tokens after the first token")
     if D != mm_projector.out_dim:
         raise ValueError(f"embedding width {D} != packer out_dim {mm_projector.out_dim}")
+    # The in-place epilogue writes below are invisible to autograd.  Whenever a gradient has to flow -- into the
+    # embedding table (LoRA / trainable embed_tokens, incl. the added vision tokens) or into trainable packers -- build
+    # the result differentiably instead: a NON-detached clone with the visual tokens assigned into their slot, which
+    # has exactly the gradient of the reference's torch.cat (lamed_arch.py:153-154).
+    needs_grad = torch.is_grad_enabled() and (
+        inputs_embeds.requires_grad or any(p.requires_grad for m in (tower, mm_projector, second)
+                                           for p in m.parameters()))
+    if needs_grad:
+        vis = pack_features(feats, mm_projector, mm_projector2)
+        out = inputs_embeds.clone(memory_format=torch.contiguous_format)
+        out[:, 1:1 + n1 + n2] = vis.to(out.dtype)
+        return out
     direct = inputs_embeds.dtype in (torch.float32, torch.bfloat16) and not (
         rt.get_precision() == "fp32_verify" and inputs_embeds.dtype != torch.float32)
     if direct:
@@ -79,7 +95,7 @@ def splice_visual_tokens(tower, mm_projector, mm_projector2, inputs_embeds, imag
         second.forward_into(feats[1], out, 1 + n1)
         return out
     # fp16 (the reference's eval autocast): pack in the activation dtype, then one cast-copy into the slot
-    vis = encode_images_with(tower, mm_projector, mm_projector2, images, images_2d)
+    vis = pack_features(feats, mm_projector, mm_projector2)
     out = inputs_embeds.detach().clone(memory_format=torch.contiguous_format)
     out[:, 1:1 + n1 + n2] = vis.to(out.dtype)
     return out

@@ -98,12 +98,21 @@ def forbid_autograd(params: Iterable[torch.Tensor], what: str) -> None:
             "or freeze the module with requires_grad_(False).")
 
 
-# ---- workspaces: one growing buffer per (device, tag); reused across calls on the same stream ---------------------
-_workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+# ---- workspaces: one growing buffer per (device, stream, tag) -----------------------------------------------------
+# Keyed on the stream the call is enqueued on (re-entrant per (device, stream)): two streams that
+# run the same stage concurrently never share scratch memory, and calls on one stream reuse theirs in stream order.
+_workspaces: Dict[Tuple[int, int, str], torch.Tensor] = {}
+_ws_lock = threading.Lock()
 
 
 def workspace(device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, int(torch.cuda.current_stream(device).cuda_stream), tag)
+    with _ws_lock:
+        return _workspace_locked(key, device, nbytes)
+
+
+def _workspace_locked(key, device, nbytes):
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
@@ -148,8 +157,9 @@ def cast_weight(w: torch.Tensor, prec: str) -> torch.Tensor:
             return w.contiguous()
         src = w.float().contiguous()
         out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-        _lib.check(_lib.load().hsenet_cast_bf16(src.data_ptr(), out.data_ptr(), src.numel(), stream_ptr(src.device)),
-                   "cast_bf16")
+        with torch.cuda.device(src.device):          # the module may live on a device that is not the current one
+            rc = _lib.load().hsenet_cast_bf16(src.data_ptr(), out.data_ptr(), src.numel(), stream_ptr(src.device))
+        _lib.check(rc, "cast_bf16")
         return out
     return w.float().contiguous()
 
@@ -158,13 +168,35 @@ def f32(p: torch.Tensor) -> torch.Tensor:
     return p.detach().float().contiguous()
 
 
+_generation = 0
+
+
+def _next_generation() -> int:
+    global _generation
+    _generation += 1
+    return _generation
+
+
 class WeightCache:
     """Derived (packed / down-cast) copies of a module's parameters, rebuilt when any parameter's storage or
-    version counter changes (load_state_dict, optimizer step, .to())."""
+    version counter changes (load_state_dict, optimizer step, .to()).
+
+    ``generation`` is a process-wide monotonically increasing number bumped on every rebuild: anything that bakes the
+    payload's device pointers in (captured CUDA graphs) validates against it -- never against ``id(payload)``, which
+    CPython reuses once the previous payload is freed.
+
+    Limitation: an in-place write through ``param.data`` (``p.data.copy_()``, EMA / clipping code, some checkpoint
+    loaders) changes neither ``data_ptr`` nor ``_version``; call ``invalidate()`` (modules expose it as
+    ``refresh_weights()``) after such an update."""
 
     def __init__(self):
         self.sig = None
         self.prec = None
+        self.payload = None
+        self.generation = 0
+
+    def invalidate(self):
+        self.sig = None
         self.payload = None
 
     def __deepcopy__(self, memo):
@@ -183,6 +215,7 @@ class WeightCache:
             self.payload = builder(prec)
             self.sig = sig
             self.prec = prec
+            self.generation = _next_generation()
         return self.payload
 
 
@@ -202,7 +235,9 @@ def kernel_launch_count() -> int:
 
 class GraphCache:
     """Captured CUDA graphs of a module's forward, keyed by the call shape; an entry is only valid for the weight-cache
-    payload and workspace address it was captured with (both are baked into the graph as raw pointers)."""
+    GENERATION and workspace address it was captured with (both are baked into the graph as raw pointers).  The entry
+    also keeps a strong reference to the payload and the workspace, so the memory a live graph points at cannot be
+    freed and re-used under it."""
 
     def __init__(self, max_entries: int = 8):
         self.entries = {}
@@ -217,17 +252,21 @@ class GraphCache:
     def __setstate__(self, state):
         self.__init__(state.get("max_entries", 8))
 
-    def get(self, key, payload_id, ws_ptr):
+    def get(self, key, generation, ws_ptr):
         ent = self.entries.get(key)
-        if ent is None or ent["_payload_id"] != payload_id or ent["_ws_ptr"] != ws_ptr:
+        if ent is None:
+            return None
+        if ent["_generation"] != generation or ent["_ws_ptr"] != ws_ptr:
+            self.entries.pop(key, None)          # stale: weights were rebuilt or the workspace moved
             return None
         return ent
 
-    def put(self, key, payload_id, ws_ptr, ent):
+    def put(self, key, generation, ws_ptr, ent, keep=()):
         if len(self.entries) >= self.max_entries and key not in self.entries:
             self.entries.pop(next(iter(self.entries)))
-        ent["_payload_id"] = payload_id
+        ent["_generation"] = generation
         ent["_ws_ptr"] = ws_ptr
+        ent["_keep"] = tuple(keep)
         self.entries[key] = ent
         return ent
 

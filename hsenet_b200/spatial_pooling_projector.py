@@ -112,9 +112,9 @@ class VisualPacker_3d_phi_v3(nn.Module):
         if prec == "fp32_verify" and out.dtype != torch.float32:
             raise ValueError("fp32_verify mode writes fp32 outputs")
         lib = _lib.load()
-        payload = self._cache.get(self.parameters(), prec, self._build_payload)
         st = rt.stream_ptr(dev)
         with torch.cuda.device(dev):
+            payload = self._cache.get(self.parameters(), prec, self._build_payload)
             # tower features arrive as a [:, 1:] view (batch stride 2049*768) or contiguous; any float dtype
             if visual_inputs.dtype == act and visual_inputs.is_contiguous():
                 hr = visual_inputs.detach()

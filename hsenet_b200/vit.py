@@ -42,8 +42,10 @@ class PatchRearrange(nn.Module):
         rt.require_cuda(x, "images")
         x = x.float().contiguous()
         out = torch.empty(x.shape[0], N_PATCH, PATCH_DIM, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().hsenet_patch_im2col(x.data_ptr(), x.shape[0], out.data_ptr(), _lib.DTYPE_F32,
-                                                   rt.stream_ptr(x.device)), "patch_im2col")
+        with torch.cuda.device(x.device):
+            rc = _lib.load().hsenet_patch_im2col(x.data_ptr(), x.shape[0], out.data_ptr(), _lib.DTYPE_F32,
+                                                 rt.stream_ptr(x.device))
+        _lib.check(rc, "patch_im2col")
         return out
 
 
@@ -207,6 +209,12 @@ class _ViTBase(nn.Module):
             w.b_score = k(rt.f32(self.patch_score_proj.bias).reshape(-1))
         return {"struct": w, "blocks": blocks, "keep": keep}
 
+    def refresh_weights(self):
+        """Drop the derived weight copies and captured graphs (call after an in-place ``param.data`` update, which the
+        (data_ptr, _version) signature of the weight cache cannot see)."""
+        self._cache.invalidate()
+        self._graphs.clear()
+
     def _run(self, x, image_2d):
         return self._finish(self._launch(x, image_2d))
 
@@ -222,8 +230,9 @@ class _ViTBase(nn.Module):
         B = x.shape[0]
         prec = rt.get_precision()
         fold = bool(self.fold_layernorm) and prec == "bf16"
-        payload = self._cache.get(self.parameters(), prec + ("+ln" if fold else ""),
-                                  lambda key: self._build_payload(prec, fold))
+        with torch.cuda.device(dev):
+            payload = self._cache.get(self.parameters(), prec + ("+ln" if fold else ""),
+                                      lambda key: self._build_payload(prec, fold))
         lib = _lib.load()
         act = rt.act_dtype(prec)
         xin = x.detach().float().contiguous()                 # reference clones its input (vit.py:455)
@@ -254,8 +263,8 @@ class _ViTBase(nn.Module):
 
         with torch.cuda.device(dev):
             if self.use_cuda_graph:
-                key = (B, prec, dev.index, want_hidden)
-                ent = self._graphs.get(key, id(payload), ws.data_ptr())
+                key = (B, prec, fold, dev.index, want_hidden, int(torch.cuda.current_stream(dev).cuda_stream))
+                ent = self._graphs.get(key, self._cache.generation, ws.data_ptr())
                 if ent is None:
                     xi = torch.empty(B, 1, *IMG_SIZE, dtype=torch.float32, device=dev)
                     si = torch.empty(B, 32, HIDDEN, dtype=torch.float32, device=dev) if self._stage == 2 else None
@@ -269,9 +278,9 @@ class _ViTBase(nn.Module):
                     n0 = lib.hsenet_launch_count()
                     with torch.cuda.graph(g):
                         launch(xi, si, *outs)
-                    ent = self._graphs.put(key, id(payload), ws.data_ptr(),
+                    ent = self._graphs.put(key, self._cache.generation, ws.data_ptr(),
                                            dict(graph=g, xi=xi, si=si, outs=outs,
-                                                kernels=int(lib.hsenet_launch_count() - n0)))
+                                                kernels=int(lib.hsenet_launch_count() - n0)), keep=(payload, ws))
                 ent["xi"].copy_(xin)
                 if ent["si"] is not None:
                     ent["si"].copy_(s2d)

@@ -122,9 +122,11 @@ const char* hsenet_error_string(int code);
 uint64_t hsenet_launch_count(void);
 
 /* Per-kernel-class CUDA-event timing (used by bench.py's roofline pass; off by default, zero cost when off).
- * Classes: 0 = tcgen05 GEMM, 1 = self attention, 2 = LayerNorm, 3 = everything else.  stop() synchronises the device
- * and fills, per class: summed milliseconds, algorithmic FLOPs, algorithmic bytes, launch count (arrays of 4). */
-#define HSENET_PROFILE_CLASSES 4
+ * Classes: 0 = tcgen05 GEMM, 1 = self attention, 2 = LayerNorm, 3 = other, 4 = packer pooling, 5 = packer window
+ * attention, 6 = patch im2col, 7 = slice cross attention, 8 = score gating, 9 = 2D-slice extraction.  stop()
+ * synchronises the device and fills, per class: summed milliseconds, algorithmic FLOPs, algorithmic bytes, launch
+ * count (arrays of HSENET_PROFILE_CLASSES). */
+#define HSENET_PROFILE_CLASSES 10
 void hsenet_profile_start(void);
 int hsenet_profile_stop(double* ms, double* flops, double* bytes, uint64_t* launches);
 

@@ -141,3 +141,57 @@ def test_odd_batches_match_oracle(cuda, B):
         with H.precision("bf16"):
             got, _ = m(x.to(cuda))
         assert_bf16(got, ref, f"B={B} bf16")
+
+
+def test_graph_cache_survives_weight_reloads_and_precision_toggles(cuda):
+    """VERDICT r1 / ADVICE: bf16 -> fp32_verify -> bf16 with weight reloads in between used to be able to replay a stale
+    graph (entries were validated by id(payload), which CPython re-uses).  Every graph-replayed result must equal a
+    graph-free run with the weights that are loaded at that moment."""
+    import hsenet_b200 as H
+    torch.manual_seed(11)
+    m = H.ViT_stage1(num_layers=1, **GEOM).eval().requires_grad_(False).to(cuda)
+    ref = H.ViT_stage1(num_layers=1, **GEOM).eval().requires_grad_(False).to(cuda)
+    ref.use_cuda_graph = False
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 1, 32, 256, 256, generator=g).to(cuda)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+    def check(tag):
+        ref.load_state_dict(m.state_dict())
+        for prec in ("bf16", "fp32_verify", "bf16"):
+            with torch.no_grad(), H.precision(prec):
+                a, _ = m(x)
+                b, _ = ref(x)
+            assert torch.equal(a, b), f"{tag}/{prec}: graph replay differs from direct launches"
+
+    check("initial")
+    for it in range(3):                                   # reload twice (and once more), toggling precision in between
+        m.load_state_dict(recipe_state_dict(shapes, seed=40 + it), strict=True)
+        check(f"reload{it}")
+        with torch.no_grad():
+            m.norm.weight.mul_(1.5)                       # optimizer-style in-place update (bumps _version)
+        check(f"inplace{it}")
+    # a write through .data is invisible to the signature: refresh_weights() is the documented escape hatch
+    m.norm.weight.data.mul_(0.5)
+    m.refresh_weights()
+    check("data-write + refresh")
+
+
+def test_report_worst_case_bf16_margin(cuda, capsys):
+    """Prints the worst bf16 max|err|/max|ref| and cosine over the 12-layer fixtures so the margin against the 2e-2 gate
+    is visible in the driver's GPU test log."""
+    import hsenet_b200 as H
+    worst = {"max_rel": 0.0, "cos": 1.0}
+    for stage, cls, seed in ((1, H.ViT_stage1, 12), (2, H.ViT_stage2, 112)):
+        g = _golden(f"vit_stage{stage}_L12.npz")
+        m = _load_recipe(cls(num_layers=12, **GEOM), seed=seed).to(cuda)
+        x, s = recipe_inputs(1)
+        with torch.no_grad(), H.precision("bf16"):
+            y, _ = m(x.to(cuda)) if stage == 1 else m(x.to(cuda), s.to(cuda))
+        mm = metrics(y[:, SAMPLE_ROWS], torch.from_numpy(g["rows"]))
+        worst["max_rel"] = max(worst["max_rel"], mm["max_rel"])
+        worst["cos"] = min(worst["cos"], mm["cos"])
+    with capsys.disabled():
+        print(f"\n[hsenet_b200] worst-case 12-layer bf16 parity vs reference fixtures: max_rel={worst['max_rel']:.4e} "
+              f"(gate 2e-2), cos={worst['cos']:.6f} (gate 0.999)")
+    assert worst["max_rel"] <= 2e-2 and worst["cos"] >= 0.999

@@ -156,10 +156,15 @@ def _attn_ref(qkv, B, S):
 
 # 2049 / 257: one scalar tail key + one scalar tail query row; 130 / 2050: two of each; 66: tail keys only;
 # 131 / 192 / 1: remainders that take the masked last step and a partial last query tile
+# 33 / 97 / 31: sequences whose last step leaves the second key half (keys 32..63 of the step) without a single valid key
+# -- the split kernel's half-B warps then carry m = -inf through the merge; 197 = the ViT-B/16 slice trunk (row f-2)
+@pytest.mark.parametrize("kernel", ["split", "rowwarp"])
 @pytest.mark.parametrize("B,S,scale", [(2, 2049, 1.0), (1, 2049, 4.0), (3, 128, 2.0), (2, 130, 1.0), (1, 1, 1.0),
-                                       (1, 257, 8.0), (2, 66, 2.0), (1, 131, 1.0), (2, 192, 3.0), (1, 2050, 2.0)])
-def test_attention_bf16(lib, cuda, B, S, scale):
+                                       (1, 257, 8.0), (2, 66, 2.0), (1, 131, 1.0), (2, 192, 3.0), (1, 2050, 2.0),
+                                       (2, 33, 2.0), (1, 97, 1.0), (3, 31, 4.0), (5, 197, 2.0)])
+def test_attention_bf16(lib, cuda, B, S, scale, kernel, monkeypatch):
     from hsenet_b200 import _lib
+    monkeypatch.setenv("HSENET_ATT_KERNEL", kernel)      # read by the launcher on every call
     g = torch.Generator().manual_seed(S + B)
     qkv = (torch.randn(B * S, 2304, generator=g) * scale).to(torch.bfloat16)
     ref = _attn_ref(qkv, B, S)

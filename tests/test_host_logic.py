@@ -108,6 +108,10 @@ def _gather_worker(rank, world, port, q):
         # no-grad variant keeps the local block differentiable (dist_utils.py:300-303)
         bi, bt = gather_features(img, txt, gather_with_grad=False, rank=rank, world_size=world)
         ok = ok and torch.equal(bi.detach(), ri.detach()) and bi.requires_grad
+        # mixed dtypes (fp32 image head output, bf16 text features under autocast): each output keeps its input's dtype
+        ci, ct = gather_features(img.detach(), txt.detach().to(torch.bfloat16), rank=rank, world_size=world)
+        ok = ok and ci.dtype == torch.float32 and ct.dtype == torch.bfloat16 and torch.equal(ci, ri.detach())
+        ok = ok and torch.equal(ct, rt_.detach().to(torch.bfloat16))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -126,18 +130,54 @@ def test_gather_features_gloo_world2():
     assert res == [(0, True), (1, True)]
 
 
-def test_graph_cache_keys_on_payload_and_workspace():
+def test_graph_cache_keys_on_generation_and_workspace():
     from hsenet_b200 import runtime as rt
     gc = rt.GraphCache(max_entries=2)
     assert gc.get(("k", 1), 10, 100) is None
-    ent = gc.put(("k", 1), 10, 100, {"graph": object()})
-    assert gc.get(("k", 1), 10, 100) is ent
+    payload = {"keep": []}
+    ent = gc.put(("k", 1), 10, 100, {"graph": object()}, keep=(payload,))
+    assert gc.get(("k", 1), 10, 100) is ent and ent["_keep"][0] is payload     # entry pins what the graph points at
     assert gc.get(("k", 1), 11, 100) is None          # weights re-packed -> captured pointers are stale
+    assert ("k", 1) not in gc.entries                 # ... and a stale entry is dropped, not kept for a later id clash
+    ent = gc.put(("k", 1), 10, 100, {"graph": object()})
     assert gc.get(("k", 1), 10, 101) is None          # workspace re-allocated
+    gc.put(("k", 1), 10, 100, {})
     gc.put(("k", 2), 10, 100, {})
     gc.put(("k", 3), 10, 100, {})                      # evicts the oldest entry
     assert len(gc.entries) == 2 and ("k", 1) not in gc.entries
     assert isinstance(copy.deepcopy(gc), rt.GraphCache) and not copy.deepcopy(gc).entries
+
+
+def test_weight_cache_generation_is_monotonic():
+    """id(payload) is reused by CPython after a rebuild (A, B, A, B ...); the generation counter never is."""
+    from hsenet_b200 import runtime as rt
+    wc = rt.WeightCache()
+    p = torch.nn.Parameter(torch.zeros(4))
+    gens = []
+    for prec in ("bf16", "fp32_verify", "bf16", "fp32_verify", "bf16"):
+        wc.get([p], prec, lambda key: {"k": key})
+        gens.append(wc.generation)
+    assert gens == sorted(gens) and len(set(gens)) == len(gens)
+    g0 = wc.generation
+    wc.get([p], "bf16", lambda key: {"k": key})
+    assert wc.generation == g0                          # unchanged weights and precision: no rebuild
+    with torch.no_grad():
+        p.add_(1.0)                                     # optimizer-style in-place update bumps _version
+    wc.get([p], "bf16", lambda key: {"k": key})
+    assert wc.generation > g0
+    g1 = wc.generation
+    p.data.mul_(2.0)                                    # invisible to (data_ptr, _version): needs invalidate()
+    wc.invalidate()
+    wc.get([p], "bf16", lambda key: {"k": key})
+    assert wc.generation > g1
+
+
+def test_gather_features_keeps_each_dtype():
+    """world == 1 returns the inputs untouched; the packing path's dtype handling is covered by the gloo worker below."""
+    import hsenet_b200 as H
+    a, b = torch.randn(2, 8), torch.randn(2, 8).to(torch.bfloat16)
+    x, y = H.gather_features(a, b)
+    assert x is a and y is b
 
 
 def test_bench_reference_arm_contract():

@@ -15,8 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(CSRC, "_build")
-LIB = os.path.join(HERE, "libhsenet_sm100a.so")
+# HSENET_BUILD_TAG=<tag> builds a variant (e.g. the trace build) beside the product library: objects in _build_<tag>/,
+# library libhsenet_sm100a_<tag>.so; select it at run time with HSENET_LIB_PATH.
+_TAG = os.environ.get("HSENET_BUILD_TAG", "")
+BUILD = os.path.join(CSRC, "_build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libhsenet_sm100a" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention_tcgen05.cu", "rowops.cu", "ingest.cu", "verify_fp32.cu"]
 HEADERS = ["common.cuh", "kernels.h", "gemm_epilogue.cuh", os.path.join("..", "..", "include", "hsenet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

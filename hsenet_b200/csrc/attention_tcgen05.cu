@@ -41,7 +41,11 @@ constexpr int K_STAGES = 3;
 constexpr int V_STAGES = 2;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int SUB_BYTES = KS * 128;        // 64 rows x 128 B
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 224;   // producer warp, two MMA-issuing warps, four softmax warps
+#ifndef HSENET_ATT_EARLY_PROBE
+#define HSENET_ATT_EARLY_PROBE 0   // measured +4 ... +9 % (slower) on all three variants: kept as a compile-time switch only
+#endif
+constexpr bool kEarlyProbe = HSENET_ATT_EARLY_PROBE != 0;
 constexpr int kDefaultPoly = 2;      // measured: 2/8 -> -2.6 %, 4/8 -> +5 % (profiles/README.md)
 constexpr int TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
@@ -51,7 +55,7 @@ struct AttBarriers {
   uint64_t q_full;
   uint64_t k_full[K_STAGES], k_empty[K_STAGES];
   uint64_t v_full[V_STAGES], v_empty[V_STAGES];
-  uint64_t s_full[2], p_full[2], pv_done[2];
+  uint64_t s_full[3], p_full[3], pv_done[2];
   uint32_t tmem_base;
 };
 
@@ -108,7 +112,15 @@ __device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float&
 }
 
 // POLY = how many of every 8 exponentials run on the FMA pipe instead of MUFU (0, 2 or 4)
-template <int POLY>
+// NBUF = number of score buffers in flight.  NBUF = 2: the round-1 layout (S0|S1|P0|P1|O).  NBUF = 3 (default since
+// round 2): three 64-column score buffers with P ALIASED onto the first 32 columns of its own scores (a thread
+// overwrites only columns it has already read into registers; Q K^T (t+3) is issued after P V (t) by the same thread, so
+// the MMA pipe orders the overwrite):    0..63 S0/P0   64..127 S1/P1   128..191 S2/P2   192..255 O.
+// Why three: tools/attn_trace.py on the two-buffer kernel shows the per-buffer cycle  softmax(t) [~1100 clk] -> p_full
+// hop [~250] -> 4 P V issues + commits [~500] -> 4 Q K^T (t+2) issues + commits [~500] -> s_full hop [~250]  = ~2650 clk
+// per TWO steps, i.e. the softmax warps are starved ~30 % of the time by the serial issue path of their own buffer.
+// With a third buffer the same cycle has three steps of softmax time to hide in.
+template <int POLY, int NBUF>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,7 +130,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   uint8_t* sV = sK + K_STAGES * TILE_BYTES;
   AttBarriers* bars = reinterpret_cast<AttBarriers*>(sV + V_STAGES * TILE_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT;
   const int h = blockIdx.y;
@@ -132,11 +144,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     mbar_init(&bars->q_full, 1);
     for (int s = 0; s < K_STAGES; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 2); }   // one commit per issuer
     for (int s = 0; s < V_STAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 2); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->p_full[i], 4);
-      mbar_init(&bars->pv_done[i], 1);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&bars->pv_done[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -146,7 +158,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
   pdl_prologue_done();      // everything above is independent of the previous kernel's output
 
   // ===================== MMA issuer of the steps t = par, par+2, ... (two threads: par = 0, 1) =====================
@@ -157,46 +169,59 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
   // implies that softmax(t) holds S[par] in registers (no s_free barrier), and since one thread's MMAs complete in order
   // s_full(t+2) implies that P V (t) has consumed P[par].  K / V stages are released by one commit from EACH thread, and
   // the P V groups of the two threads are kept in step order (deterministic accumulation into O).
+  // TMEM column of score buffer b / of the packed probabilities of buffer b
+  auto col_s = [](int b) -> uint32_t { return static_cast<uint32_t>(b * KS); };
+  auto col_p = [](int b) -> uint32_t { return NBUF == 3 ? static_cast<uint32_t>(b * KS) : COL_P + static_cast<uint32_t>(b * 32); };
   auto mma_issuer = [&](const int par) {
     constexpr uint32_t idesc_qk = make_idesc_bf16(QT, KS, 0, 0);          // S[128q x 64k] = Q K^T
     constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);    // O[128q x 64d] += P V (V MN-major)
     const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
     auto issue_qk = [&](const int t) {                                    // k_full of its tile already waited for
-      const int ks = (t >> 1) % K_STAGES;
-      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + par * SUB_BYTES));
+      const int ks = (t >> 1) % K_STAGES, b = t % NBUF;
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + (t & 1) * SUB_BYTES));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < kHeadDim / 16; ++k)
-        umma_ss(tmem_base + COL_S + par * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-      tc_commit(&bars->s_full[par]);
-      tc_commit(&bars->k_empty[ks]);
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss(tmem_base + col_s(b), qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        tc_commit(&bars->s_full[b]);
+        tc_commit(&bars->k_empty[ks]);
+      }
+      __syncwarp();
     };
-    if (par >= nsub) return;
-    mbar_wait(&bars->q_full, 0);
-    mbar_wait(&bars->k_full[0], 0);
-    issue_qk(par);
+    // Step t is served by thread (t & 1): P V (t), then Q K^T (t + NBUF) into the buffer P V (t) has just read.
+    // Prologue: Q K^T (s), s < NBUF, is issued by the thread that would have issued it in the loop, thread ((s - NBUF) & 1),
+    // so that every 128-key K tile is released by exactly one commit from each thread.
+    mbar_wait_nocall(&bars->q_full, 0);
+    for (int s0 = 0; s0 < NBUF && s0 < nsub; ++s0) {
+      if (((s0 + NBUF) & 1) != par) continue;
+      mbar_wait_nocall(&bars->k_full[(s0 >> 1) % K_STAGES], 0);
+      issue_qk(s0);
+    }
     ATT_TR_DECL;
     for (int t = par; t < nsub; t += 2) {
-      const int j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
+      const int j = t >> 1, vs = j % V_STAGES, t2 = t + NBUF, b = t % NBUF;
       // operands of this iteration's MMAs first: long satisfied, kept off the critical path
-      mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
-      if (t2 < nsub) mbar_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+      mbar_wait_nocall(&bars->v_full[vs], (j / V_STAGES) & 1);
+      if (t2 < nsub) mbar_wait_nocall(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
       // P V (t-1), issued by the other thread, must have retired before P V (t) is issued: both accumulate into the same
       // fp32 tile, and an occasional swap of two accumulations would make the last bits differ from run to run (and
       // P V (0) initialises O).  It retires long before p_full(t) arrives, so this wait is off the critical path too.
-      if (t >= 1) mbar_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);
+      if (t >= 1) mbar_wait_nocall(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);
       ATT_TR(0);
-      mbar_wait(&bars->p_full[par], (t >> 1) & 1);          // softmax t done: P[par] stored, S[par] in registers
+      mbar_wait_nocall(&bars->p_full[b], (t / NBUF) & 1);          // softmax t done: P[b] stored, S[b] in registers
       tc_fence_after();
       ATT_TR(1);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < KS / 16; ++k) {
-        // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes = +128 (16-byte units)
-        umma_ts(tmem_base + COL_O, tmem_base + COL_P + par * 32 + 8 * k, vdesc + 128 * k, idesc_pv,
-                (t | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < KS / 16; ++k) {
+          // A: 16 keys = 8 TMEM columns of packed bf16 pairs; B: 16 key rows = 2048 bytes = +128 (16-byte units)
+          umma_ts(tmem_base + COL_O, tmem_base + col_p(b) + 8 * k, vdesc + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&bars->pv_done[par]);
+        tc_commit(&bars->v_empty[vs]);
       }
-      tc_commit(&bars->pv_done[par]);
-      tc_commit(&bars->v_empty[vs]);
+      __syncwarp();
       ATT_TR(2);
       if (t2 < nsub) issue_qk(t2);
       ATT_TR(3);
@@ -204,27 +229,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     ATT_TR_DUMP(16 + 16 * par);
   };
 
+  // Roles are whole WARPS that stay convergent; the single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) sit
+  // inside elect_one() regions.  Round 1 ran each role as one lane of a diverged warp ("if (lane == 0)"): ptxas then
+  // wraps every instruction that takes uniform-register operands (UTCHMMA, UTCBAR, UTMALDG, SYNCS) in a per-lane
+  // ELECT / R2UR.BROADCAST / BRA.U.ANY loop -- ~100 issue cycles per 32-cycle MMA (cuobjdump of the round-1 kernel).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer =====================
+    if (elect_one()) {
       mbar_arrive_expect_tx(&bars->q_full, TILE_BYTES);
       tma_load_2d(sQ, &tmQKV, &bars->q_full, h * kHeadDim, row0 + q0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int ks = j % K_STAGES, vs = j % V_STAGES;
-        mbar_wait(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    // K runs one tile ahead of V: Q K^T is issued up to three steps before the P V of the same keys, and a K stage
+    // is released that much earlier than the V stage of the same tile -- loading K(j+1) only after V(j) had found
+    // its stage free (the round-1 order) left the K tile two steps of lead, less than a TMA round trip under load
+    auto load_k = [&](const int j) {
+      const int ks = j % K_STAGES;
+      mbar_wait_nocall(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], TILE_BYTES);
         tma_load_2d_hint(sK + ks * TILE_BYTES, &tmQKV, &bars->k_full[ks], kHidden + h * kHeadDim, row0 + j * KT,
                          kEvictLast);
-        mbar_wait(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+      }
+      __syncwarp();
+    };
+    load_k(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int vs = j % V_STAGES;
+      if (j + 1 < ntiles) load_k(j + 1);
+      mbar_wait_nocall(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
         tma_load_2d_hint(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * kHidden + h * kHeadDim,
                          row0 + j * KT, kEvictLast);
       }
-    } else if (lane == 1) {
-      mma_issuer(1);
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) mma_issuer(0);
+    mma_issuer(0);
+  } else if (warp == 2) {
+    mma_issuer(1);
   } else {
     // ===================== softmax / correction / epilogue warps =====================
     const int quarter = warp & 3;
@@ -234,23 +278,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     const float c = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
     float m = -INFINITY;                                 // running reference max (log2 domain, already scaled)
     float l = 0.f;
+    bool s_ready = false;                                // result of the early probe of the NEXT step's s_full barrier
     ATT_TR_DECL;
     // one 64-key step; MASKED (compile time) only for a last step that runs past the end of the sequence -- kept out
     // of the main loop on purpose: left as a run-time test the compiler turns the 64 per-key checks into selects that
     // execute on EVERY step (195 of ~530 instructions per step in the first version)
     auto softmax_step = [&](const int t, auto masked) {
-      const int bsel = t & 1;
-      mbar_wait(&bars->s_full[bsel], (t >> 1) & 1);      // S[bsel] ready and P[bsel] free
+      const int bsel = t % NBUF;
+      // S[bsel] ready and P[bsel] free.  The barrier was already probed during the previous step (below): even a
+      // satisfied mbarrier probe takes ~250-300 cycles to return, which is otherwise exposed at the top of every step.
+      if (!s_ready) mbar_wait_nocall(&bars->s_full[bsel], (t / NBUF) & 1);
       tc_fence_after();
       ATT_TR(0);
       uint32_t x[64];
       uint32_t pk[32];
       float alpha = 1.f;
       if (warp_live) {
-        tmem_ld32(tmem_base + lane_base + COL_S + bsel * KS, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
-        tmem_ld32(tmem_base + lane_base + COL_S + bsel * KS + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
-        tmem_ld_wait();
+        tmem_ld32(tmem_base + lane_base + col_s(bsel), *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
+        tmem_ld32(tmem_base + lane_base + col_s(bsel) + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
       }
+      s_ready = kEarlyProbe && (t + 1 < nsub) && mbar_try_wait(&bars->s_full[(t + 1) % NBUF], ((t + 1) / NBUF) & 1);
+      if (warp_live) tmem_ld_wait();
       ATT_TR(1);
       ATT_TR(2);
       if (warp_live) {
@@ -298,13 +346,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         unpack2(rs2, rs0, rs1);
         l = l * alpha + (rs0 + rs1);
         ATT_TR(4);
-        tmem_st32(tmem_base + lane_base + COL_P + bsel * 32, pk);
+        tmem_st32(tmem_base + lane_base + col_p(bsel), pk);
         ATT_TR(5);
       }
       // O correction (rare after the first steps): P V (t-1) must have retired before O is rescaled
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
-        if (t >= 2) mbar_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);   // the other issuing thread's P V (t-2)
+        mbar_wait_nocall(&bars->pv_done[(t & 1) ^ 1], ((t - 1) >> 1) & 1);
+        if (t >= 2) mbar_wait_nocall(&bars->pv_done[t & 1], ((t >> 1) - 1) & 1);   // the other issuing thread's P V (t-2)
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll 1
@@ -326,10 +374,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     const bool ragged = (S % KS) != 0;
     for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
     if (ragged) softmax_step(nsub - 1, std::true_type{});
-    if (warp == 2 && lane == 0) { ATT_TR_DUMP(0); }
+    if (warp == 3 && lane == 0) { ATT_TR_DUMP(0); }
     // ---- epilogue: O / l -> bf16 -> out[b*S + qi, h*64 .. h*64+63] -----------------------------------------------
-    if (nsub >= 2) mbar_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
-    mbar_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
+    if (nsub >= 2) mbar_wait_nocall(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
+    mbar_wait_nocall(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
     uint32_t o[32];
@@ -376,7 +424,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
 // orders the overwrite), which keeps the CTA at 256 TMEM columns and two CTAs per SM:
 //     TMEM columns   0.. 63  S0 (P0_A at 0..15, P0_B at 32..47)    64..127  S1 (P1_A, P1_B)    128..191 O_A    192..255 O_B
 // Issuing threads, TMA rings and the step-parity protocol are those of the kernel above; p_full counts 8 warps.
-constexpr int ATS_THREADS = 320;
+constexpr int ATS_THREADS = 352;   // producer warp, two MMA-issuing warps, eight softmax warps
 constexpr uint32_t ATS_COL_S = 0, ATS_COL_O = 128;
 constexpr int ATS_SMEM = ATT_SMEM + 2 * 128 * 8;
 
@@ -391,7 +439,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
   AttBarriers* bars = reinterpret_cast<AttBarriers*>(sV + V_STAGES * TILE_BYTES);
   float2* ml = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 halves][128 rows] (m, l)
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT;
   const int h = blockIdx.y;
@@ -419,7 +467,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
   pdl_prologue_done();
 
   auto mma_issuer = [&](const int par) {
@@ -429,61 +477,86 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     auto issue_qk = [&](const int t) {
       const int ks = (t >> 1) % K_STAGES;
       const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + par * SUB_BYTES));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < kHeadDim / 16; ++k)
-        umma_ss(tmem_base + ATS_COL_S + par * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-      tc_commit(&bars->s_full[par]);
-      tc_commit(&bars->k_empty[ks]);
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss(tmem_base + ATS_COL_S + par * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        tc_commit(&bars->s_full[par]);
+        tc_commit(&bars->k_empty[ks]);
+      }
+      __syncwarp();
     };
     if (par >= nsub) return;
-    mbar_wait(&bars->q_full, 0);
-    mbar_wait(&bars->k_full[0], 0);
+    mbar_wait_nocall(&bars->q_full, 0);
+    mbar_wait_nocall(&bars->k_full[0], 0);
     issue_qk(par);
+    ATT_TR_DECL;
     for (int t = par; t < nsub; t += 2) {
       const int j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
-      mbar_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
-      if (t2 < nsub) mbar_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
-      if (t >= 1) mbar_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);   // keep the accumulation order fixed
-      mbar_wait(&bars->p_full[par], (t >> 1) & 1);
+      mbar_wait_nocall(&bars->v_full[vs], (j / V_STAGES) & 1);
+      if (t2 < nsub) mbar_wait_nocall(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+      if (t >= 1) mbar_wait_nocall(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);   // keep the accumulation order fixed
+      ATT_TR(0);
+      mbar_wait_nocall(&bars->p_full[par], (t >> 1) & 1);
       tc_fence_after();
+      ATT_TR(1);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < KS / 16; ++k) {
-        // key half k>>1: A = 16 keys = 8 packed columns at the start of that half's score columns, D = that half's O
-        const int half = k >> 1;
-        umma_ts(tmem_base + ATS_COL_O + half * kHeadDim, tmem_base + ATS_COL_S + par * KS + half * 32 + 8 * (k & 1),
-                vdesc + 128 * k, idesc_pv, (t | (k & 1)) != 0 ? 1u : 0u);
+        for (int k = 0; k < KS / 16; ++k) {
+          // key half k>>1: A = 16 keys = 8 packed columns at the start of that half's score columns, D = that half's O
+          const int half = k >> 1;
+          umma_ts(tmem_base + ATS_COL_O + half * kHeadDim, tmem_base + ATS_COL_S + par * KS + half * 32 + 8 * (k & 1),
+                  vdesc + 128 * k, idesc_pv, (t | (k & 1)) != 0 ? 1u : 0u);
+        }
+        tc_commit(&bars->pv_done[par]);
+        tc_commit(&bars->v_empty[vs]);
       }
-      tc_commit(&bars->pv_done[par]);
-      tc_commit(&bars->v_empty[vs]);
+      __syncwarp();
+      ATT_TR(2);
       if (t2 < nsub) issue_qk(t2);
+      ATT_TR(3);
     }
+    ATT_TR_DUMP(16 + 16 * par);
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer (whole warp, elect-guarded issue; K one tile ahead of V -- see attention_kernel)
+    if (elect_one()) {
       mbar_arrive_expect_tx(&bars->q_full, TILE_BYTES);
       tma_load_2d(sQ, &tmQKV, &bars->q_full, h * kHeadDim, row0 + q0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int ks = j % K_STAGES, vs = j % V_STAGES;
-        mbar_wait(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    auto load_k = [&](const int j) {
+      const int ks = j % K_STAGES;
+      mbar_wait_nocall(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], TILE_BYTES);
         tma_load_2d_hint(sK + ks * TILE_BYTES, &tmQKV, &bars->k_full[ks], kHidden + h * kHeadDim, row0 + j * KT,
                          kEvictLast);
-        mbar_wait(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+      }
+      __syncwarp();
+    };
+    load_k(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int vs = j % V_STAGES;
+      if (j + 1 < ntiles) load_k(j + 1);
+      mbar_wait_nocall(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
         tma_load_2d_hint(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * kHidden + h * kHeadDim,
                          row0 + j * KT, kEvictLast);
       }
-    } else if (lane == 1) {
-      mma_issuer(1);
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) mma_issuer(0);
+    mma_issuer(0);
+  } else if (warp == 2) {
+    mma_issuer(1);
   } else {
     // ===================== softmax warps: quarter = TMEM lane quarter (warp % 4), half = key half =====================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 3) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const int qi = q0 + quarter * 32 + lane;
     const bool warp_live = (q0 + quarter * 32) < S;
@@ -491,17 +564,22 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     const uint32_t col_o = ATS_COL_O + half * kHeadDim;
     float m = -INFINITY;
     float l = 0.f;
+    bool s_ready = false;
+    ATT_TR_DECL;
     auto softmax_step = [&](const int t, auto masked) {
       const int bsel = t & 1;
       const uint32_t col_s = ATS_COL_S + bsel * KS + half * 32;
-      mbar_wait(&bars->s_full[bsel], (t >> 1) & 1);
+      if (!s_ready) mbar_wait_nocall(&bars->s_full[bsel], (t >> 1) & 1);
       tc_fence_after();
+      ATT_TR(0);
       uint32_t x[32];
       uint32_t pk[16];
       float alpha = 1.f;
+      if (warp_live) tmem_ld32(tmem_base + lane_base + col_s, x);
+      s_ready = kEarlyProbe && (t + 1 < nsub) && mbar_try_wait(&bars->s_full[bsel ^ 1], ((t + 1) >> 1) & 1);
       if (warp_live) {
-        tmem_ld32(tmem_base + lane_base + col_s, x);
         tmem_ld_wait();
+        ATT_TR(1);
         if constexpr (decltype(masked)::value) {
           const int kbase = t * KS + half * 32;
 #pragma unroll
@@ -521,6 +599,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
           alpha = ex2(m - tm);
           m = tm;
         }
+        ATT_TR(3);
         // a half that has not seen a valid key yet (only possible in a masked step) keeps m = -inf: subtract 0 instead,
         // so that the all -inf scores give exp2(-inf) = 0 and not exp2(-inf + inf)
         float msub = m;
@@ -546,11 +625,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         float rs0, rs1;
         unpack2(rs2, rs0, rs1);
         l = l * alpha + (rs0 + rs1);
+        ATT_TR(4);
         tmem_st16(tmem_base + lane_base + col_s, pk);
+        ATT_TR(5);
       }
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
-        if (t >= 2) mbar_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
+        mbar_wait_nocall(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
+        if (t >= 2) mbar_wait_nocall(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll 1
@@ -562,14 +643,17 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
           tmem_st32(tmem_base + lane_base + col_o + ch * 32, o);
         }
       }
+      ATT_TR(6);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
+      ATT_TR(7);
     };
     const bool ragged = (S % KS) != 0;
     for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
     if (ragged) softmax_step(nsub - 1, std::true_type{});
+    if (warp == 3 && lane == 0) { ATT_TR_DUMP(0); }
     // ---- merge the two key halves and store: this warp takes output columns [half*32, half*32+32) of its 32 rows ----
     ml[half * 128 + quarter * 32 + lane] = make_float2(m, l);
     asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 softmax warps only
@@ -579,8 +663,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     const float inv = 1.0f / (l * w_self + other.y * w_other);
     const float fa = (half == 0 ? w_self : w_other) * inv;          // weight of O_A
     const float fb = (half == 0 ? w_other : w_self) * inv;          // weight of O_B
-    if (nsub >= 2) mbar_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
-    mbar_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
+    if (nsub >= 2) mbar_wait_nocall(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
+    mbar_wait_nocall(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
     tc_fence_after();
     uint32_t oa[32], ob[32];
     tmem_ld32(tmem_base + lane_base + ATS_COL_O + half * 32, oa);
@@ -623,9 +707,12 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
   static unsigned char attr_set[kMaxDevices] = {0};
   if (first_use_on_device(attr_set)) {
     bool ok = true;
-    ok &= cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attention_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attention_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attention_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attention_split_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM) == cudaSuccess;
@@ -635,17 +722,24 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
                  stream);
   const char* e = std::getenv("HSENET_ATT_POLY");        // share of exponentials emulated on the FMA pipe (0 / 2 / 4 of 8)
   const int poly = e != nullptr ? std::atoi(e) : kDefaultPoly;
-  const char* kv = std::getenv("HSENET_ATT_KERNEL");     // "rowwarp" = the round-1 kernel (4 softmax warps), for A/B runs
-  const bool split = !(kv != nullptr && kv[0] == 'r');
+  // HSENET_ATT_KERNEL (A/B runs): "tri" (default) = 4 softmax warps, three aliased S/P buffers; "rowwarp" = the round-1
+  // kernel (two S + two P buffers); "split" = 8 softmax warps splitting every step by key half (two O accumulators)
+  const char* kv = std::getenv("HSENET_ATT_KERNEL");
+  const bool split = kv != nullptr && kv[0] == 's';
+  const bool tri = !(kv != nullptr && kv[0] == 'r');
   const dim3 grid((S + QT - 1) / QT, kHeads, B);
   if (split) {
     if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
     else if (poly >= 2) launch_pdl(attention_split_kernel<2>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
     else launch_pdl(attention_split_kernel<0>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
+  } else if (tri) {
+    if (poly >= 4) launch_pdl(attention_kernel<4, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    else if (poly >= 2) launch_pdl(attention_kernel<2, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    else launch_pdl(attention_kernel<0, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
   } else {
-    if (poly >= 4) launch_pdl(attention_kernel<4>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-    else if (poly >= 2) launch_pdl(attention_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-    else launch_pdl(attention_kernel<0>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    if (poly >= 4) launch_pdl(attention_kernel<4, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    else if (poly >= 2) launch_pdl(attention_kernel<2, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    else launch_pdl(attention_kernel<0, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;

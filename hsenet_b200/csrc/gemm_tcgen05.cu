@@ -56,7 +56,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_epi = smem_u32(smem + STAGES * STAGE_BYTES);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int n_tiles = N / BN;
   const int m_tiles = (M + BM - 1) / BM;
@@ -83,54 +83,57 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
   pdl_prologue_done();      // everything above is independent of the previous kernel's output
 
+  // producer / issuer: convergent warps with elect_one()-guarded issue (see gemm_tcgen05_2cta.cu)
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM;
-        const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->empty[s], phase ^ 1);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_nocall(&bars->empty[s], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
           tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmA, &bars->full[s], kb * BK, m0);
           tma_load_2d_hint(smem_b + s * B_STAGE_BYTES, &tmB, &bars->full[s], kb * BK, n0, kEvictLast);
-          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int s = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int s = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait_nocall(&bars->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_nocall(&bars->full[s], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->full[s], phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
+        const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
             umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tc_commit(&bars->empty[s]);
-          if (++s == STAGES) { s = 0; phase ^= 1; }
+          if (kb == k_blocks - 1) tc_commit(&bars->tmem_full[acc]);
         }
-        tc_commit(&bars->tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue warps =====================

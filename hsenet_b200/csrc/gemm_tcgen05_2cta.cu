@@ -114,7 +114,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t smem_epi = smem_u32(smem + STAGES * STAGE_BYTES);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();       // 0 = leader (issues the MMAs)
   const int pair = blockIdx.x >> 1;
@@ -141,19 +141,23 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
   pdl_prologue_done();      // everything above is independent of the previous kernel's output
 
+  // The producer and the MMA issuer are whole WARPS that stay convergent, with the single-thread instructions inside
+  // elect_one() regions: as single lanes of a diverged warp ("if (lane == 0)", round 1) every instruction that takes
+  // uniform-register operands (UTMALDG, UTCHMMA, UTCBAR, SYNCS) was wrapped by ptxas in an ELECT / R2UR.BROADCAST /
+  // BRA.U.ANY loop.
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        const int m0 = (tile / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
-        const int n0 = (tile % n_tiles) * PN + static_cast<int>(cta_rank) * 128;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->empty[s], phase ^ 1);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int m0 = (tile / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
+      const int n0 = (tile % n_tiles) * PN + static_cast<int>(cta_rank) * 128;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_nocall(&bars->empty[s], phase ^ 1);
+        if (elect_one()) {
           if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
           tma_load_2d_2cta(smem_a + s * A_STAGE_BYTES, &tmA, &bars->full[s], kb * BK, m0, kEvictNormal);
           tma_load_2d_2cta(smem_b + s * B_STAGE_BYTES, &tmB, &bars->full[s], kb * BK, n0, kEvictLast);
@@ -161,38 +165,42 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                            kEvictNormal);
           tma_load_2d_2cta(smem_b + s * B_STAGE_BYTES + SUB_BYTES, &tmB, &bars->full[s], kb * BK + 64, n0,
                            kEvictLast);
-          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (cta_rank == 0 && lane == 0) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(PM, PN, 0, 0);
       int s = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_nocall(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&bars->full[s], phase);
+          mbar_wait_nocall(&bars->full[s], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
           // 8 MMAs per barrier round trip (an mbarrier wait costs ~250 cycles, as much as two of these MMAs):
           // k = 0..3 walk the first swizzled sub-tile (+32 B each), k = 4..7 the second (+16 KB = 1024 x 16 B)
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint32_t off = (k >> 2) * (SUB_BYTES >> 4) + 2 * (k & 3);
-            umma_ss_2cta(tmem_d, adesc + off, bdesc + off, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t off = (k >> 2) * (SUB_BYTES >> 4) + 2 * (k & 3);
+              umma_ss_2cta(tmem_d, adesc + off, bdesc + off, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit_2cta(&bars->empty[s]);
+            if (kb == k_blocks - 1) tc_commit_2cta(&bars->tmem_full[acc]);
           }
-          tc_commit_2cta(&bars->empty[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
-        tc_commit_2cta(&bars->tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -158,7 +158,7 @@ def _attn_ref(qkv, B, S):
 # 131 / 192 / 1: remainders that take the masked last step and a partial last query tile
 # 33 / 97 / 31: sequences whose last step leaves the second key half (keys 32..63 of the step) without a single valid key
 # -- the split kernel's half-B warps then carry m = -inf through the merge; 197 = the ViT-B/16 slice trunk (row f-2)
-@pytest.mark.parametrize("kernel", ["split", "rowwarp"])
+@pytest.mark.parametrize("kernel", ["tri", "split", "rowwarp"])
 @pytest.mark.parametrize("B,S,scale", [(2, 2049, 1.0), (1, 2049, 4.0), (3, 128, 2.0), (2, 130, 1.0), (1, 1, 1.0),
                                        (1, 257, 8.0), (2, 66, 2.0), (1, 131, 1.0), (2, 192, 3.0), (1, 2050, 2.0),
                                        (2, 33, 2.0), (1, 97, 1.0), (3, 31, 4.0), (5, 197, 2.0)])

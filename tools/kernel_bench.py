@@ -61,6 +61,29 @@ def main():
         "fc1   768->3072 (+bias+gelu bf16)": (lambda: lin(xn, 768, w1, 3072, b3072, None, 1, None, hid), 2.0 * M * 3072 * 768),
         "fc2  3072->768  (+bias+resid fp32)": (lambda: lin(hid, 3072, w2, 768, b768, x32, 0, x32, None), 2.0 * M * 768 * 3072),
     }
+    # cuBLASLt beside every shape (torch.nn.functional.linear, bf16 in / bf16 out, bias fused by cuBLASLt where there is
+    # one; the residual add / GELU / fp32 output of our epilogues are NOT included -- it is the bare-GEMM bar to beat)
+    import torch.nn.functional as F
+    lt = {
+        "qkv   768->2304 (bf16 out)": lambda: F.linear(xn, wqkv),
+        "out   768->768  (+bias+resid fp32)": lambda: F.linear(att, wout, b768.to(bf)),
+        "fc1   768->3072 (+bias+gelu bf16)": lambda: F.linear(xn, w1, b3072.to(bf)),
+        "fc2  3072->768  (+bias+resid fp32)": lambda: F.linear(hid, w2, b768.to(bf)),
+    }
+    b768b, b3072b = b768.to(bf), b3072.to(bf)
+    lt = {
+        "qkv   768->2304 (bf16 out)": lambda: F.linear(xn, wqkv),
+        "out   768->768  (+bias+resid fp32)": lambda: F.linear(att, wout, b768b),
+        "fc1   768->3072 (+bias+gelu bf16)": lambda: F.linear(xn, w1, b3072b),
+        "fc2  3072->768  (+bias+resid fp32)": lambda: F.linear(hid, w2, b768b),
+    }
+    tot_t, tot_f = 0.0, 0.0
+    for name, (fn, fl) in cases.items():
+        us = timeit(lt[name], args.iters)
+        tot_t += us
+        tot_f += fl
+        print(f"[cuBLASLt bare GEMM] {name:38s} {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
+    print(f"[cuBLASLt bare GEMM] layer GEMMs total {tot_t:8.1f} us  {tot_f / tot_t / 1e6:7.1f} TFLOP/s")
     for variant in ("2cta", "1cta"):
         os.environ["HSENET_GEMM_1CTA"] = "1" if variant == "1cta" else "0"
         tot_t, tot_f = 0.0, 0.0

@@ -37,6 +37,32 @@ class PackerWeights(C.Structure):
         (n, vp) for n in ("w_q", "b_q", "w_kv", "b_kv", "w_o", "b_o", "ln_g", "ln_b", "w_p0", "b_p0", "w_p2", "b_p2")]
 
 
+class BlockWeightsT(C.Structure):
+    _fields_ = [(n, vp) for n in ("w_qkv_t", "w_out_t", "w_fc1_t", "w_fc2_t")]
+
+
+class VitWeightsT(C.Structure):
+    _fields_ = [(n, vp) for n in ("blocks_host", "w_sq_t", "w_so_t")]
+
+
+class BlockGrads(C.Structure):
+    _fields_ = [(n, vp) for n in ("w_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+                                  "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class VitGrads(C.Structure):
+    _fields_ = [(n, vp) for n in ("blocks_host", "cls_token", "pos_embed", "w_patch", "b_patch", "norm_g", "norm_b",
+                                  "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score")]
+
+
+class PackerWeightsT(C.Structure):
+    _fields_ = [(n, vp) for n in ("w_q_t", "w_kv_t", "w_o_t", "w_p0_t", "w_p2_t")]
+
+
+class PackerGrads(C.Structure):
+    _fields_ = [(n, vp) for n in ("w_q", "b_q", "w_kv", "b_kv", "w_o", "b_o", "ln_g", "ln_b", "w_p0", "b_p0", "w_p2", "b_p2")]
+
+
 # name -> (restype, argtypes); mirrors include/hsenet_b200.h one to one (tests/test_abi.py checks the header).
 SIGNATURES = {
     "hsenet_version": (C.c_char_p, []),
@@ -71,6 +97,22 @@ SIGNATURES = {
     "hsenet_foreground_bbox": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "hsenet_crop_normalize_resize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "hsenet_fold_layernorm": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    # training path
+    "hsenet_transpose_weight": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "hsenet_vit_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hsenet_vit_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hsenet_vit_forward_train": (C.c_int, [C.POINTER(VitWeights), vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t,
+                                           vp, C.c_size_t, vp]),
+    "hsenet_vit_backward": (C.c_int, [C.POINTER(VitWeights), C.POINTER(VitWeightsT), vp, C.c_int, C.c_int, vp, vp, vp,
+                                      C.c_size_t, C.POINTER(VitGrads), vp, C.c_size_t, vp]),
+    "hsenet_packer_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hsenet_packer_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hsenet_packer_forward_train": (C.c_int, [C.POINTER(PackerWeights), vp, C.c_int, C.c_int, vp, vp, C.c_size_t, vp,
+                                              C.c_size_t, vp]),
+    "hsenet_packer_backward": (C.c_int, [C.POINTER(PackerWeights), C.POINTER(PackerWeightsT), vp, C.c_int, C.c_int, vp,
+                                         vp, C.c_size_t, C.POINTER(PackerGrads), vp, vp, C.c_size_t, vp]),
+    "hsenet_self_attention_train": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "hsenet_self_attention_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }
 
 _lib = None

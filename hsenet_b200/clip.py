@@ -32,7 +32,10 @@ class ClipImageHead(nn.Module):
 def clip_image_head(tokens: torch.Tensor, proj: nn.Linear, cache: rt.WeightCache | None = None) -> torch.Tensor:
     """tokens [B,2049,768] (act dtype of the current precision) -> unit-norm cls embeddings fp32 [B,768]."""
     rt.require_cuda(tokens, "tokens")
-    rt.forbid_autograd(proj.parameters(), "clip_image_head")
+    if torch.is_grad_enabled() and (tokens.requires_grad or any(p.requires_grad for p in proj.parameters())):
+        # training (CLIP_stage1.py:100-101,117): 1.2 MFLOP on the cls row -- plain autograd ops, like the logits
+        cls = tokens[:, 0].float()
+        return F.normalize(F.linear(cls, proj.weight.float(), proj.bias.float()), dim=-1)
     prec = rt.get_precision()
     act = rt.act_dtype(prec)
     if tokens.dim() != 3 or tokens.shape[1] != 2049 or tokens.shape[2] != 768:

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "composite.cuh"
 #include "kernels.h"
 
 #include <cstdlib>
@@ -98,56 +99,6 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64
 }
 
 namespace {
-
-constexpr size_t kAlign = 1024;
-inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
-
-struct Bump {
-  uint8_t* base;
-  size_t off = 0;
-  explicit Bump(void* p) : base(static_cast<uint8_t*>(p)) {}
-  template <typename T>
-  T* take(size_t count) {
-    T* p = reinterpret_cast<T*>(base + off);
-    off += align_up(count * sizeof(T));
-    return p;
-  }
-};
-
-template <typename T>
-struct Prec;
-template <>
-struct Prec<__nv_bfloat16> {
-  static int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
-                  cudaStream_t s) {
-    return gemm_bf16(A, lda, W, ldw, M, N, K, ep, s);
-  }
-  static int attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, cudaStream_t s) {
-    return attention_bf16(qkv, out, B, S, s);
-  }
-};
-template <>
-struct Prec<float> {
-  static int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
-                  cudaStream_t s) {
-    return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, M, N, K, ep, s);
-  }
-  static int attention(const float* qkv, float* out, int B, int S, cudaStream_t s) {
-    return attention_f32(qkv, out, B, S, s);
-  }
-};
-
-template <typename T>
-inline void set_act_out(GemmEpilogue& ep, T* p, int ld) {
-  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p);
-  ep.ld_bf16 = ld;
-}
-
-#define HS_TRY(expr)                 \
-  do {                               \
-    const int _rc = (expr);          \
-    if (_rc != HS_OK) return _rc;    \
-  } while (0)
 
 constexpr int kMaxFusedLayers = 32;    // statistics slots in the workspace; deeper layers keep the LayerNorm kernel
 constexpr float kLnEps = 1e-5f;        // nn.LayerNorm default (same constant as layernorm_rows)
@@ -270,7 +221,7 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
         HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
       }
     }
-    HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, B, kSeq, st));
+    HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, nullptr, B, kSeq, st));
     {
       GemmEpilogue ep;   // out_proj + residual
       ep.bias = bw.b_out; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
@@ -522,9 +473,9 @@ int hsenet_self_attention(const void* qkv, void* out, int B, int S, int precisio
   if (qkv == nullptr || out == nullptr) return HSENET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == HSENET_PREC_BF16)
-    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, S, st);
+    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), nullptr, B, S, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
-    return attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), B, S, st);
+    return attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), nullptr, B, S, st);
   return HSENET_ERR_ARG;
 }
 

@@ -43,9 +43,32 @@ constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-sw
 constexpr int SUB_BYTES = KS * 128;        // 64 rows x 128 B
 constexpr int ATT_THREADS = 224;   // producer warp, two MMA-issuing warps, four softmax warps
 #ifndef HSENET_ATT_EARLY_PROBE
-#define HSENET_ATT_EARLY_PROBE 0   // measured +4 ... +9 % (slower) on all three variants: kept as a compile-time switch only
+#define HSENET_ATT_EARLY_PROBE 0   // measured slower in both forms (register result: +4..9 %, deferred named predicate: +3..7 %)
 #endif
 constexpr bool kEarlyProbe = HSENET_ATT_EARLY_PROBE != 0;
+#ifndef HSENET_ATT_PARK
+#define HSENET_ATT_PARK 1
+#endif
+// Deferred mbarrier probe: the try_wait writes a NAMED PTX predicate (declared once per kernel by ATT_PROBE_DECL) and
+// returns immediately; the predicate is only read by att_probe_result() one step later, so the ~250-300 cycles a
+// (satisfied) probe takes to come back overlap the exponentials instead of sitting at the top of every step.
+#define ATT_PROBE_DECL asm volatile(".reg .pred att_pnext;\n\tsetp.ne.b32 att_pnext, 0, 0;" ::: "memory")
+__device__ __forceinline__ void att_probe_issue(uint64_t* bar, uint32_t parity) {
+  asm volatile("mbarrier.try_wait.parity.shared::cta.b64 att_pnext, [%0], %1;" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void att_probe_clear() { asm volatile("setp.ne.b32 att_pnext, 0, 0;" ::: "memory"); }
+__device__ __forceinline__ bool att_probe_result() {
+  uint32_t ok;
+  asm volatile("selp.b32 %0, 1, 0, att_pnext;" : "=r"(ok)::"memory");
+  return ok != 0;
+}
+// waits of the producer / issuer warps (1 = parked try_wait with a suspend-time hint, 2 = also the softmax warps)
+__device__ __forceinline__ void ctl_wait(uint64_t* bar, uint32_t parity) {
+  if (HSENET_ATT_PARK >= 1) mbar_wait_parked(bar, parity); else mbar_wait_nocall(bar, parity);
+}
+__device__ __forceinline__ void smx_wait(uint64_t* bar, uint32_t parity) {
+  if (HSENET_ATT_PARK >= 2) mbar_wait_parked(bar, parity); else mbar_wait_nocall(bar, parity);
+}
 constexpr int kDefaultPoly = 2;      // measured: 2/8 -> -2.6 %, 4/8 -> +5 % (profiles/README.md)
 constexpr int TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
@@ -122,7 +145,8 @@ __device__ __forceinline__ void exp2_poly2(float y0, float y1, float& e0, float&
 // With a third buffer the same cycle has three steps of softmax time to hide in.
 template <int POLY, int NBUF>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S) {
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                 int S) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -191,24 +215,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     // Step t is served by thread (t & 1): P V (t), then Q K^T (t + NBUF) into the buffer P V (t) has just read.
     // Prologue: Q K^T (s), s < NBUF, is issued by the thread that would have issued it in the loop, thread ((s - NBUF) & 1),
     // so that every 128-key K tile is released by exactly one commit from each thread.
-    mbar_wait_nocall(&bars->q_full, 0);
+    ctl_wait(&bars->q_full, 0);
     for (int s0 = 0; s0 < NBUF && s0 < nsub; ++s0) {
       if (((s0 + NBUF) & 1) != par) continue;
-      mbar_wait_nocall(&bars->k_full[(s0 >> 1) % K_STAGES], 0);
+      ctl_wait(&bars->k_full[(s0 >> 1) % K_STAGES], 0);
       issue_qk(s0);
     }
     ATT_TR_DECL;
     for (int t = par; t < nsub; t += 2) {
       const int j = t >> 1, vs = j % V_STAGES, t2 = t + NBUF, b = t % NBUF;
       // operands of this iteration's MMAs first: long satisfied, kept off the critical path
-      mbar_wait_nocall(&bars->v_full[vs], (j / V_STAGES) & 1);
-      if (t2 < nsub) mbar_wait_nocall(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+      ctl_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+      if (t2 < nsub) ctl_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
       // P V (t-1), issued by the other thread, must have retired before P V (t) is issued: both accumulate into the same
       // fp32 tile, and an occasional swap of two accumulations would make the last bits differ from run to run (and
       // P V (0) initialises O).  It retires long before p_full(t) arrives, so this wait is off the critical path too.
-      if (t >= 1) mbar_wait_nocall(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);
+      if (t >= 1) ctl_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);
       ATT_TR(0);
-      mbar_wait_nocall(&bars->p_full[b], (t / NBUF) & 1);          // softmax t done: P[b] stored, S[b] in registers
+      ctl_wait(&bars->p_full[b], (t / NBUF) & 1);          // softmax t done: P[b] stored, S[b] in registers
       tc_fence_after();
       ATT_TR(1);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
@@ -245,7 +269,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     // its stage free (the round-1 order) left the K tile two steps of lead, less than a TMA round trip under load
     auto load_k = [&](const int j) {
       const int ks = j % K_STAGES;
-      mbar_wait_nocall(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+      ctl_wait(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], TILE_BYTES);
         tma_load_2d_hint(sK + ks * TILE_BYTES, &tmQKV, &bars->k_full[ks], kHidden + h * kHeadDim, row0 + j * KT,
@@ -257,7 +281,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     for (int j = 0; j < ntiles; ++j) {
       const int vs = j % V_STAGES;
       if (j + 1 < ntiles) load_k(j + 1);
-      mbar_wait_nocall(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+      ctl_wait(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
         tma_load_2d_hint(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * kHidden + h * kHeadDim,
@@ -278,7 +302,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     const float c = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
     float m = -INFINITY;                                 // running reference max (log2 domain, already scaled)
     float l = 0.f;
-    bool s_ready = false;                                // result of the early probe of the NEXT step's s_full barrier
+    if constexpr (kEarlyProbe) ATT_PROBE_DECL;           // named predicate: result of the early probe of the NEXT step
     ATT_TR_DECL;
     // one 64-key step; MASKED (compile time) only for a last step that runs past the end of the sequence -- kept out
     // of the main loop on purpose: left as a run-time test the compiler turns the 64 per-key checks into selects that
@@ -287,7 +311,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       const int bsel = t % NBUF;
       // S[bsel] ready and P[bsel] free.  The barrier was already probed during the previous step (below): even a
       // satisfied mbarrier probe takes ~250-300 cycles to return, which is otherwise exposed at the top of every step.
-      if (!s_ready) mbar_wait_nocall(&bars->s_full[bsel], (t / NBUF) & 1);
+      if constexpr (kEarlyProbe) {
+        if (!att_probe_result()) smx_wait(&bars->s_full[bsel], (t / NBUF) & 1);
+      } else {
+        smx_wait(&bars->s_full[bsel], (t / NBUF) & 1);
+      }
       tc_fence_after();
       ATT_TR(0);
       uint32_t x[64];
@@ -297,7 +325,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
         tmem_ld32(tmem_base + lane_base + col_s(bsel), *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
         tmem_ld32(tmem_base + lane_base + col_s(bsel) + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
       }
-      s_ready = kEarlyProbe && (t + 1 < nsub) && mbar_try_wait(&bars->s_full[(t + 1) % NBUF], ((t + 1) / NBUF) & 1);
+      if constexpr (kEarlyProbe) {
+        if (t + 1 < nsub) att_probe_issue(&bars->s_full[(t + 1) % NBUF], ((t + 1) / NBUF) & 1);
+        else att_probe_clear();
+      }
       if (warp_live) tmem_ld_wait();
       ATT_TR(1);
       ATT_TR(2);
@@ -351,8 +382,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       }
       // O correction (rare after the first steps): P V (t-1) must have retired before O is rescaled
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait_nocall(&bars->pv_done[(t & 1) ^ 1], ((t - 1) >> 1) & 1);
-        if (t >= 2) mbar_wait_nocall(&bars->pv_done[t & 1], ((t >> 1) - 1) & 1);   // the other issuing thread's P V (t-2)
+        smx_wait(&bars->pv_done[(t & 1) ^ 1], ((t - 1) >> 1) & 1);
+        if (t >= 2) smx_wait(&bars->pv_done[t & 1], ((t >> 1) - 1) & 1);   // the other issuing thread's P V (t-2)
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll 1
@@ -376,10 +407,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     if (ragged) softmax_step(nsub - 1, std::true_type{});
     if (warp == 3 && lane == 0) { ATT_TR_DUMP(0); }
     // ---- epilogue: O / l -> bf16 -> out[b*S + qi, h*64 .. h*64+63] -----------------------------------------------
-    if (nsub >= 2) mbar_wait_nocall(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
-    mbar_wait_nocall(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
+    if (nsub >= 2) smx_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
+    smx_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
+    // training forward: log2-domain log-sum-exp of the scaled scores, lse = m + log2(l), so that the backward kernels
+    // rebuild P = 2^(s c - lse) without a second pass; rows past the sequence end get +inf (their P is then exactly 0)
+    if (lse_out != nullptr) {
+      const int sp = ((S + QT - 1) / QT) * QT;
+      lse_out[(static_cast<long>(b) * kHeads + h) * sp + qi] = qi < S ? m + log2f(l) : INFINITY;
+    }
     uint32_t o[32];
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
@@ -430,7 +467,8 @@ constexpr int ATS_SMEM = ATT_SMEM + 2 * 128 * 8;
 
 template <int POLY>
 __global__ void __launch_bounds__(ATS_THREADS, 2)
-attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S) {
+attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ lse_out, int S) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -487,17 +525,17 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       __syncwarp();
     };
     if (par >= nsub) return;
-    mbar_wait_nocall(&bars->q_full, 0);
-    mbar_wait_nocall(&bars->k_full[0], 0);
+    ctl_wait(&bars->q_full, 0);
+    ctl_wait(&bars->k_full[0], 0);
     issue_qk(par);
     ATT_TR_DECL;
     for (int t = par; t < nsub; t += 2) {
       const int j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
-      mbar_wait_nocall(&bars->v_full[vs], (j / V_STAGES) & 1);
-      if (t2 < nsub) mbar_wait_nocall(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
-      if (t >= 1) mbar_wait_nocall(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);   // keep the accumulation order fixed
+      ctl_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+      if (t2 < nsub) ctl_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+      if (t >= 1) ctl_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);   // keep the accumulation order fixed
       ATT_TR(0);
-      mbar_wait_nocall(&bars->p_full[par], (t >> 1) & 1);
+      ctl_wait(&bars->p_full[par], (t >> 1) & 1);
       tc_fence_after();
       ATT_TR(1);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
@@ -529,7 +567,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     __syncwarp();
     auto load_k = [&](const int j) {
       const int ks = j % K_STAGES;
-      mbar_wait_nocall(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
+      ctl_wait(&bars->k_empty[ks], ((j / K_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], TILE_BYTES);
         tma_load_2d_hint(sK + ks * TILE_BYTES, &tmQKV, &bars->k_full[ks], kHidden + h * kHeadDim, row0 + j * KT,
@@ -541,7 +579,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     for (int j = 0; j < ntiles; ++j) {
       const int vs = j % V_STAGES;
       if (j + 1 < ntiles) load_k(j + 1);
-      mbar_wait_nocall(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
+      ctl_wait(&bars->v_empty[vs], ((j / V_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], TILE_BYTES);
         tma_load_2d_hint(sV + vs * TILE_BYTES, &tmQKV, &bars->v_full[vs], 2 * kHidden + h * kHeadDim,
@@ -564,19 +602,23 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     const uint32_t col_o = ATS_COL_O + half * kHeadDim;
     float m = -INFINITY;
     float l = 0.f;
-    bool s_ready = false;
+    if constexpr (kEarlyProbe) ATT_PROBE_DECL;
     ATT_TR_DECL;
     auto softmax_step = [&](const int t, auto masked) {
       const int bsel = t & 1;
       const uint32_t col_s = ATS_COL_S + bsel * KS + half * 32;
-      if (!s_ready) mbar_wait_nocall(&bars->s_full[bsel], (t >> 1) & 1);
+      if constexpr (kEarlyProbe) {
+        if (!att_probe_result()) smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
+      } else {
+        smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
+      }
       tc_fence_after();
       ATT_TR(0);
       uint32_t x[32];
       uint32_t pk[16];
       float alpha = 1.f;
       if (warp_live) tmem_ld32(tmem_base + lane_base + col_s, x);
-      s_ready = kEarlyProbe && (t + 1 < nsub) && mbar_try_wait(&bars->s_full[bsel ^ 1], ((t + 1) >> 1) & 1);
+      // (two buffers: s_full(t+1) completes while this step's exponentials run, so the probe is issued after them)
       if (warp_live) {
         tmem_ld_wait();
         ATT_TR(1);
@@ -629,9 +671,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         tmem_st16(tmem_base + lane_base + col_s, pk);
         ATT_TR(5);
       }
+      if constexpr (kEarlyProbe) {
+        if (t + 1 < nsub) att_probe_issue(&bars->s_full[bsel ^ 1], ((t + 1) >> 1) & 1);
+        else att_probe_clear();
+      }
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        mbar_wait_nocall(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
-        if (t >= 2) mbar_wait_nocall(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
+        smx_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
+        if (t >= 2) smx_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll 1
@@ -660,11 +706,16 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     const float2 other = ml[(half ^ 1) * 128 + quarter * 32 + lane];
     const float ms = fmaxf(m, other.x);
     const float w_self = ex2(m - ms), w_other = ex2(other.x - ms);
-    const float inv = 1.0f / (l * w_self + other.y * w_other);
+    const float lsum = l * w_self + other.y * w_other;
+    const float inv = 1.0f / lsum;
+    if (lse_out != nullptr && half == 0) {
+      const int sp = ((S + QT - 1) / QT) * QT;
+      lse_out[(static_cast<long>(b) * kHeads + h) * sp + qi] = qi < S ? ms + log2f(lsum) : INFINITY;
+    }
     const float fa = (half == 0 ? w_self : w_other) * inv;          // weight of O_A
     const float fb = (half == 0 ? w_other : w_self) * inv;          // weight of O_B
-    if (nsub >= 2) mbar_wait_nocall(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
-    mbar_wait_nocall(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
+    if (nsub >= 2) smx_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
+    smx_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
     tc_fence_after();
     uint32_t oa[32], ob[32];
     tmem_ld32(tmem_base + lane_base + ATS_COL_O + half * 32, oa);
@@ -698,7 +749,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
 
 }  // namespace
 
-int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, cudaStream_t stream) {
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int S, cudaStream_t stream) {
   if (B <= 0 || S <= 0) return HS_OK;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return HS_ERR_ALIGN;
   CUtensorMap tm;
@@ -729,17 +780,17 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, c
   const bool tri = !(kv != nullptr && kv[0] == 'r');
   const dim3 grid((S + QT - 1) / QT, kHeads, B);
   if (split) {
-    if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
-    else if (poly >= 2) launch_pdl(attention_split_kernel<2>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
-    else launch_pdl(attention_split_kernel<0>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, S);
+    if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);
+    else if (poly >= 2) launch_pdl(attention_split_kernel<2>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);
+    else launch_pdl(attention_split_kernel<0>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);
   } else if (tri) {
-    if (poly >= 4) launch_pdl(attention_kernel<4, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-    else if (poly >= 2) launch_pdl(attention_kernel<2, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-    else launch_pdl(attention_kernel<0, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    if (poly >= 4) launch_pdl(attention_kernel<4, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
+    else if (poly >= 2) launch_pdl(attention_kernel<2, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
+    else launch_pdl(attention_kernel<0, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
   } else {
-    if (poly >= 4) launch_pdl(attention_kernel<4, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-    else if (poly >= 2) launch_pdl(attention_kernel<2, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
-    else launch_pdl(attention_kernel<0, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, S);
+    if (poly >= 4) launch_pdl(attention_kernel<4, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
+    else if (poly >= 2) launch_pdl(attention_kernel<2, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
+    else launch_pdl(attention_kernel<0, 2>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;

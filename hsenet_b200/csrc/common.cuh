@@ -84,6 +84,27 @@ __device__ __forceinline__ void mbar_wait_nocall(uint64_t* bar, uint32_t parity)
   }
 }
 
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires)
+// instead of returning after the short default limit, so a waiting control warp stops consuming the issue slots of the
+// compute warps that share its scheduler (ncu: 28 % of the attention kernel's issued instructions were polling loops).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 20)) __trap();
+  }
+}
+
 // Same, with a nanosleep back-off between polls: for single-thread producer / issuer roles whose polling would
 // otherwise steal issue slots from the compute warps that share their SM sub-partition.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
@@ -241,6 +262,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// d/dx of the exact GELU: Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 
 // ---- packed fp32x2 helpers (sm_100 FFMA2 / FADD2: two fp32 lanes per issued instruction) -------------------------
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {

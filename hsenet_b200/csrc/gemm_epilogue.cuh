@@ -30,7 +30,7 @@ enum : int { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32_RESID = 2, EPI_GENERIC = 3
 constexpr int EPI_WARP_BYTES = 32 * 128;   // one 32x32 fp32 block per epilogue warp
 
 __host__ inline int epilogue_mode(const GemmEpilogue& ep) {
-  const bool plain = ep.rows_per_group == 0 && ep.row_add == nullptr;
+  const bool plain = ep.rows_per_group == 0 && ep.row_add == nullptr && ep.dgelu_src == nullptr;
   if (plain && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.resid == nullptr && ep.stats_out == nullptr) {
     if (ep.stats_in != nullptr) return ep.gelu ? EPI_BF16_GELU_LN : EPI_BF16_LN;
     return ep.gelu ? EPI_BF16_GELU : EPI_BF16;
@@ -274,6 +274,13 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
           x.w += bias4.w + ra[it].w + rs[it].w;
           if (ep.gelu) {
             x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w);
+          }
+          if (ep.dgelu_src != nullptr) {      // backward of GELU: multiply by gelu'(saved pre-activation)
+            const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(ep.dgelu_src) +
+                                                            orow[it] * ep.ld_dgelu + col);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            x.x *= gelu_erf_grad(a.x); x.y *= gelu_erf_grad(a.y); x.z *= gelu_erf_grad(b.x); x.w *= gelu_erf_grad(b.y);
           }
           if (ep.out_f32 != nullptr) *reinterpret_cast<float4*>(ep.out_f32 + orow[it] * ep.ld_f32 + col) = x;
           if (ep.out_bf16 != nullptr) {

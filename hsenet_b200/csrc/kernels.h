@@ -35,6 +35,10 @@ struct GemmEpilogue {
   int rows_per_group = 0;
   int group_stride = 0;
   int group_offset = 0;
+  // backward of GELU fused into the GEMM that produces the gradient of the hidden activation (generic epilogue only):
+  //   v *= gelu'(dgelu_src[orow, col]),  dgelu_src = the saved PRE-activation in the activation dtype (bf16 / fp32)
+  const void* dgelu_src = nullptr;
+  int ld_dgelu = 0;
   // LayerNorm folded into the GEMMs on either side of it (gemm_epilogue.cuh):
   float2* stats_out = nullptr;        // producer (EPI_F32_RESID): += (sum, sum of squares) of every output row
   const float2* stats_in = nullptr;   // consumer (EPI_BF16[_GELU]): row statistics of the un-normalised A operand
@@ -91,8 +95,16 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int
 
 // ---- self attention over the 3D token sequence (MONAI SABlock core) --------------------------------------------
 // qkv [B*S, 2304] with feature order (qkv, head, d); out [B*S, 768] heads concatenated.
-int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, cudaStream_t stream);
-int attention_f32(const float* qkv, float* out, int B, int S, cudaStream_t stream);
+// lse (optional, training forward): [B, 12, S_pad] fp32 with S_pad = ceil(S/128)*128, log2-domain log-sum-exp of the scaled
+// scores (m + log2 l); entries S <= q < S_pad are written as +inf.
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int S, cudaStream_t stream);
+int attention_f32(const float* qkv, float* out, float* lse, int B, int S, cudaStream_t stream);
+// Backward of the fused attention (recompute style: P is rebuilt from qkv and lse).  d_out [B*S,768] (gradient of the
+// re-concatenated heads), out [B*S,768] (the forward result) -> d_qkv [B*S,2304].  dvec: scratch [B,12,S_pad] fp32.
+int attention_bwd_bf16(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* d_out, const float* lse,
+                       float* dvec, __nv_bfloat16* d_qkv, int B, int S, cudaStream_t stream);
+int attention_bwd_f32(const float* qkv, const float* out, const float* d_out, const float* lse, float* dvec, float* d_qkv,
+                      int B, int S, cudaStream_t stream);
 
 // ---- row kernels ------------------------------------------------------------------------------------------------
 template <typename OutT>
@@ -138,6 +150,34 @@ int l2_normalize_rows(const float* in, float* out, int rows, int dim, cudaStream
 // ---- 2D slice extraction (vit.py:529-531) ---------------------------------------------------------------------------
 template <typename OutT>
 int slice_extract(const float* vol, OutT* out, int B, int out_h, int out_w, cudaStream_t stream);
+
+// ---- training path: row kernels of the backward pass (backward.cu) -----------------------------------------------------
+int padded_rows(int M);                       // ceil(M / 128) * 128
+// in [M,N] (row stride ld_in) -> out_t [N, padded_rows(M)] (zero padded), optional cast copy [M,N] (ld_copy), optional exact GELU
+// applied first, optional per-64-row-tile column sums colsum_partial [padded_rows(M)/64, N] (finish with colsum_finish)
+template <typename TIn, typename TOut>
+int transpose_pad(const TIn* in, long ld_in, int M, int N, TOut* out_t, TOut* copy_out, long ld_copy, int gelu,
+                  float* colsum_partial, cudaStream_t st);
+int colsum_finish(const float* partial, int T, int N, float* out, cudaStream_t st);
+template <typename T>
+int gelu_rows(const T* in, T* out, long n, cudaStream_t st);
+int layernorm_bwd_blocks(long rows);          // number of partial rows layernorm_bwd / score_scale_bwd write
+int layernorm_bwd(const float* dy, const float* x, long ldx, const float* gamma, long rows, float* dx, long ld_dx,
+                  int accumulate, float* dgamma_partial, float* dbeta_partial, cudaStream_t st);
+template <typename T>
+int combine_final_grad(const T* d_tokens, const T* d_patch, int B, int seq, float* dy, cudaStream_t st);
+int sum_over_batch(const float* in, long batch_stride, int B, int rows, float* out, cudaStream_t st);
+template <typename T>
+int window_attn_bwd(const T* dO, const float* Q, const T* KV, float* dQ, T* dKV, int B, cudaStream_t st);
+template <typename TG>
+int pool_bwd(const TG* dLR, float* dHR, int B, int accumulate, cudaStream_t st);
+template <typename T>
+int slice_xattn_bwd(const float* Q, const float* KV, const T* dO, float* dQ, int accumulate, float* P, float* dS,
+                    float* dKV, int B, cudaStream_t st);
+int score_scale_bwd(const float* dX, const float* XP, const float* Z, const float* g, const float* be, const float* ws,
+                    const float* scores, float* dXP, float* dZ, float* dg_partial, float* db_partial,
+                    float* dws_partial, float* dbs_partial, int B, cudaStream_t st);
+int add_rows(float* out, const float* a, long n, cudaStream_t st);
 
 // integer maps (device-computed, for bit-exact tests against the oracle's closed forms)
 int patch_gather_map(int32_t* out, cudaStream_t stream);      // [2048,1024]

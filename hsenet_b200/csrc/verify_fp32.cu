@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       if (ep.gelu) {
         x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
       }
+      if (ep.dgelu_src != nullptr) {
+        const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.dgelu_src) + orow * ep.ld_dgelu + col);
+        x.x *= gelu_erf_grad(a.x); x.y *= gelu_erf_grad(a.y); x.z *= gelu_erf_grad(a.z); x.w *= gelu_erf_grad(a.w);
+      }
       if (ep.out_f32 != nullptr) *reinterpret_cast<float4*>(ep.out_f32 + orow * ep.ld_f32 + col) = x;
       if (out_act != nullptr) *reinterpret_cast<float4*>(out_act + orow * ep.ld_bf16 + col) = x;
     }
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 // fp32 flash attention on CUDA cores: one thread per query row, 32-key shared-memory tiles.
 constexpr int AQ = 128, AK = 32;
 __global__ void __launch_bounds__(AQ) attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                           int S) {
+                                                           float* __restrict__ lse_out, int S) {
   __shared__ float4 sK[AK][kHeadDim / 4];
   __shared__ float4 sV[AK][kHeadDim / 4];
   const int b = blockIdx.z, h = blockIdx.y;
@@ -178,6 +182,10 @@ __global__ void __launch_bounds__(AQ) attention_f32_kernel(const float* __restri
     }
     m = mn;
   }
+  if (lse_out != nullptr) {      // log2-domain log-sum-exp of the scaled scores (same convention as the tcgen05 kernel)
+    const int sp = ((S + 127) / 128) * 128;
+    if (qi < sp) lse_out[(static_cast<long>(b) * kHeads + h) * sp + qi] = qi < S ? (m + logf(l)) * 1.4426950408889634f : INFINITY;
+  }
   if (qi < S) {
     const float inv = 1.0f / l;
     float4* op = reinterpret_cast<float4*>(out + (base + qi) * kHidden + h * kHeadDim);
@@ -186,7 +194,155 @@ __global__ void __launch_bounds__(AQ) attention_f32_kernel(const float* __restri
   }
 }
 
+// ---- fp32 attention backward on CUDA cores (verification mode): P is rebuilt from qkv and the saved log-sum-exp ----
+//   P = 2^(s c - lse),  dP = dO V^T,  dS = P o (dP - D) / 8,  dQ = dS K,  dK = dS^T Q,  dV = P^T dO,  D = rowsum(dO o O)
+constexpr float kAttC = 0.125f * 1.4426950408889634f;
+// dQ: one thread per query row (q, dO row and the dQ accumulator in registers), 32-key shared-memory tiles
+__global__ void __launch_bounds__(AQ) attention_bwd_dq_f32_kernel(const float* __restrict__ qkv,
+                                                                  const float* __restrict__ d_out,
+                                                                  const float* __restrict__ lse,
+                                                                  const float* __restrict__ dvec,
+                                                                  float* __restrict__ d_qkv, int S) {
+  __shared__ float4 sK[AK][kHeadDim / 4];
+  __shared__ float4 sV[AK][kHeadDim / 4];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int qi = blockIdx.x * AQ + threadIdx.x;
+  const int qrow = qi < S ? qi : S - 1;
+  const long base = static_cast<long>(b) * S;
+  const int ld = 3 * kHidden;
+  const int sp = ((S + 127) / 128) * 128;
+  float4 q[kHeadDim / 4], go[kHeadDim / 4], dq[kHeadDim / 4];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (base + qrow) * ld + h * kHeadDim);
+    const float4* gp = reinterpret_cast<const float4*>(d_out + (base + qrow) * kHidden + h * kHeadDim);
+#pragma unroll
+    for (int i = 0; i < kHeadDim / 4; ++i) {
+      q[i] = __ldg(qp + i);
+      go[i] = __ldg(gp + i);
+      dq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float l2 = lse[(static_cast<long>(b) * kHeads + h) * sp + qrow];
+  const float dv = dvec[(static_cast<long>(b) * kHeads + h) * sp + qrow];
+  for (int k0 = 0; k0 < S; k0 += AK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < AK * (kHeadDim / 4); i += AQ) {
+      const int j = i / (kHeadDim / 4), c = i % (kHeadDim / 4);
+      const int kr = k0 + j < S ? k0 + j : S - 1;
+      const float* src = qkv + (base + kr) * ld + h * kHeadDim;
+      sK[j][c] = __ldg(reinterpret_cast<const float4*>(src + kHidden) + c);
+      sV[j][c] = __ldg(reinterpret_cast<const float4*>(src + 2 * kHidden) + c);
+    }
+    __syncthreads();
+    for (int j = 0; j < AK && k0 + j < S; ++j) {
+      float sd = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < kHeadDim / 4; ++i) {
+        const float4 k = sK[j][i], v = sV[j][i];
+        sd = fmaf(q[i].x, k.x, sd); sd = fmaf(q[i].y, k.y, sd); sd = fmaf(q[i].z, k.z, sd); sd = fmaf(q[i].w, k.w, sd);
+        dp = fmaf(go[i].x, v.x, dp); dp = fmaf(go[i].y, v.y, dp); dp = fmaf(go[i].z, v.z, dp); dp = fmaf(go[i].w, v.w, dp);
+      }
+      const float p = exp2f(sd * kAttC - l2);
+      const float ds = p * (dp - dv) * 0.125f;
+#pragma unroll
+      for (int i = 0; i < kHeadDim / 4; ++i) {
+        const float4 k = sK[j][i];
+        dq[i].x = fmaf(ds, k.x, dq[i].x); dq[i].y = fmaf(ds, k.y, dq[i].y);
+        dq[i].z = fmaf(ds, k.z, dq[i].z); dq[i].w = fmaf(ds, k.w, dq[i].w);
+      }
+    }
+  }
+  if (qi < S) {
+    float4* op = reinterpret_cast<float4*>(d_qkv + (base + qi) * ld + h * kHeadDim);
+#pragma unroll
+    for (int i = 0; i < kHeadDim / 4; ++i) op[i] = dq[i];
+  }
+}
+
+// dK (WHICH = 0) or dV (WHICH = 1): one thread per key row, 32-query shared-memory tiles of Q and dO
+template <int WHICH>
+__global__ void __launch_bounds__(AQ) attention_bwd_dkv_f32_kernel(const float* __restrict__ qkv,
+                                                                   const float* __restrict__ d_out,
+                                                                   const float* __restrict__ lse,
+                                                                   const float* __restrict__ dvec,
+                                                                   float* __restrict__ d_qkv, int S) {
+  __shared__ float4 sQ[AK][kHeadDim / 4];
+  __shared__ float4 sG[AK][kHeadDim / 4];
+  __shared__ float sL[AK], sD[AK];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int ki = blockIdx.x * AQ + threadIdx.x;
+  const int krow = ki < S ? ki : S - 1;
+  const long base = static_cast<long>(b) * S;
+  const int ld = 3 * kHidden;
+  const int sp = ((S + 127) / 128) * 128;
+  float4 k[kHeadDim / 4], v[kHeadDim / 4], acc[kHeadDim / 4];
+  {
+    const float* src = qkv + (base + krow) * ld + h * kHeadDim;
+#pragma unroll
+    for (int i = 0; i < kHeadDim / 4; ++i) {
+      k[i] = __ldg(reinterpret_cast<const float4*>(src + kHidden) + i);
+      v[i] = __ldg(reinterpret_cast<const float4*>(src + 2 * kHidden) + i);
+      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (int q0 = 0; q0 < S; q0 += AK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < AK * (kHeadDim / 4); i += AQ) {
+      const int j = i / (kHeadDim / 4), c = i % (kHeadDim / 4);
+      const int qr = q0 + j < S ? q0 + j : S - 1;
+      sQ[j][c] = __ldg(reinterpret_cast<const float4*>(qkv + (base + qr) * ld + h * kHeadDim) + c);
+      sG[j][c] = __ldg(reinterpret_cast<const float4*>(d_out + (base + qr) * kHidden + h * kHeadDim) + c);
+    }
+    if (threadIdx.x < AK) {
+      const int qr = q0 + threadIdx.x < S ? q0 + threadIdx.x : S - 1;
+      sL[threadIdx.x] = lse[(static_cast<long>(b) * kHeads + h) * sp + qr];
+      sD[threadIdx.x] = dvec[(static_cast<long>(b) * kHeads + h) * sp + qr];
+    }
+    __syncthreads();
+    for (int j = 0; j < AK && q0 + j < S; ++j) {
+      float sd = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < kHeadDim / 4; ++i) {
+        const float4 q = sQ[j][i];
+        sd = fmaf(q.x, k[i].x, sd); sd = fmaf(q.y, k[i].y, sd); sd = fmaf(q.z, k[i].z, sd); sd = fmaf(q.w, k[i].w, sd);
+        if (WHICH == 0) {
+          const float4 g = sG[j][i];
+          dp = fmaf(g.x, v[i].x, dp); dp = fmaf(g.y, v[i].y, dp); dp = fmaf(g.z, v[i].z, dp); dp = fmaf(g.w, v[i].w, dp);
+        }
+      }
+      const float p = exp2f(sd * kAttC - sL[j]);
+      const float w = WHICH == 0 ? p * (dp - sD[j]) * 0.125f : p;
+#pragma unroll
+      for (int i = 0; i < kHeadDim / 4; ++i) {
+        const float4 x = WHICH == 0 ? sQ[j][i] : sG[j][i];
+        acc[i].x = fmaf(w, x.x, acc[i].x); acc[i].y = fmaf(w, x.y, acc[i].y);
+        acc[i].z = fmaf(w, x.z, acc[i].z); acc[i].w = fmaf(w, x.w, acc[i].w);
+      }
+    }
+  }
+  if (ki < S) {
+    float4* op = reinterpret_cast<float4*>(d_qkv + (base + ki) * ld + (WHICH == 0 ? kHidden : 2 * kHidden) + h * kHeadDim);
+#pragma unroll
+    for (int i = 0; i < kHeadDim / 4; ++i) op[i] = acc[i];
+  }
+}
+
 }  // namespace
+
+int attention_rowdot_f32(const float* out, const float* d_out, float* dvec, int B, int S, cudaStream_t stream);
+
+int attention_bwd_f32(const float* qkv, const float* out, const float* d_out, const float* lse, float* dvec, float* d_qkv,
+                      int B, int S, cudaStream_t stream) {
+  if (B <= 0 || S <= 0) return HS_OK;
+  const int rc = attention_rowdot_f32(out, d_out, dvec, B, S, stream);
+  if (rc != HS_OK) return rc;
+  const dim3 grid((S + AQ - 1) / AQ, kHeads, B);
+  attention_bwd_dq_f32_kernel<<<grid, AQ, 0, stream>>>(qkv, d_out, lse, dvec, d_qkv, S);
+  attention_bwd_dkv_f32_kernel<0><<<grid, AQ, 0, stream>>>(qkv, d_out, lse, dvec, d_qkv, S);
+  attention_bwd_dkv_f32_kernel<1><<<grid, AQ, 0, stream>>>(qkv, d_out, lse, dvec, d_qkv, S);
+  count_launch(); count_launch(); count_launch();
+  return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
+}
 
 int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
              cudaStream_t stream) {
@@ -199,9 +355,9 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
 }
 
-int attention_f32(const float* qkv, float* out, int B, int S, cudaStream_t stream) {
+int attention_f32(const float* qkv, float* out, float* lse, int B, int S, cudaStream_t stream) {
   if (B <= 0 || S <= 0) return HS_OK;
-  attention_f32_kernel<<<dim3((S + AQ - 1) / AQ, kHeads, B), AQ, 0, stream>>>(qkv, out, S);
+  attention_f32_kernel<<<dim3((S + AQ - 1) / AQ, kHeads, B), AQ, 0, stream>>>(qkv, out, lse, S);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
 }

@@ -27,6 +27,10 @@ def pack_features(feats, mm_projector, mm_projector2, out_dtype=None):
         second = mm_projector2 if mm_projector2 is not None else mm_projector   # fallback of lamed_arch.py:128-131
         n1, n2 = mm_projector.proj_out_num, second.proj_out_num
         dt = out_dtype or mm_projector.output_dtype or rt.act_dtype()
+        if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad or any(
+                p.requires_grad for m in (mm_projector, second) for p in m.parameters())):
+            # training: the packers run through their autograd Functions; the concatenation is the reference's
+            return torch.cat([mm_projector(f1), second(f2)], dim=1).to(dt)
         out = torch.empty(f1.shape[0], n1 + n2, mm_projector.out_dim, dtype=dt, device=f1.device)
         mm_projector.forward_into(f1, out, 0)
         second.forward_into(f2, out, n1)

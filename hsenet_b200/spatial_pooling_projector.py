@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from . import runtime as rt
+from . import training as tr
 
 HIDDEN = 768
 N_PATCH = 2048
@@ -61,6 +62,54 @@ class VisualPacker_3d_phi_v3(nn.Module):
         #: dtype of the returned tokens; None = activation dtype of the precision mode
         self.output_dtype = None
         self._cache = rt.WeightCache()
+        self._train_cache = rt.WeightCache()
+
+    def disable_dropout(self):
+        """Set p = 0 on the two Dropout members of resolution_attention (the kernels do not apply dropout)."""
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
+        return self
+
+    def refresh_weights(self):
+        self._cache.invalidate()
+        self._train_cache.invalidate()
+
+    def _build_train_payload(self, prec: str):
+        pl = self._build_payload(prec)
+        keep = pl["keep"]
+
+        def kt(w):
+            t = tr.transpose_weight(w, prec)
+            keep.append(t)
+            return t.data_ptr()
+
+        a = self.resolution_attention
+        wt = _lib.PackerWeightsT()
+        wt.w_q_t = kt(a.Wq.weight)
+        wt.w_kv_t = kt(torch.cat([a.Wk.weight.detach(), a.Wv.weight.detach()], 0))
+        wt.w_o_t = kt(a.output_linear.weight)
+        wt.w_p0_t = kt(self.proj_mpls[0].weight)
+        wt.w_p2_t = kt(self.proj_mpls[2].weight)
+        pl["struct_t"] = wt
+        return pl
+
+    def _check_dropout(self):
+        if self.training and self.resolution_attention.dropout.p > 0:
+            raise NotImplementedError(
+                "VisualPacker_3d_phi_v3 in .train() mode applies Dropout(p=0.1) inside resolution_attention "
+                "(spatial_pooling_projector.py:58-59); the hsenet_b200 kernels do not apply dropout -- call .eval() "
+                "or .disable_dropout() (p = 0)")
+
+    def _forward_train(self, visual_inputs):
+        rt.require_cuda(visual_inputs, "visual_inputs")
+        self._check_dropout()
+        if visual_inputs.dim() != 3 or visual_inputs.shape[1] != N_PATCH or visual_inputs.shape[2] != HIDDEN:
+            raise ValueError(f"expected visual_inputs [B,2048,768], got {tuple(visual_inputs.shape)}")
+        out = tr.PackerTrainFn.apply(self, visual_inputs, *self.parameters())
+        if self.output_dtype is not None and out.dtype != self.output_dtype:
+            out = out.to(self.output_dtype)
+        return out
 
     @property
     def proj_out_num(self):
@@ -93,11 +142,10 @@ class VisualPacker_3d_phi_v3(nn.Module):
         """Pack ``visual_inputs [B,2048,768]`` into ``out[:, token_offset:token_offset+128, :]`` (``out`` is
         ``[B, T, out_dim]`` contiguous, fp32 or bf16).  Used by encode_images to skip the reference's torch.cat."""
         rt.require_cuda(visual_inputs, "visual_inputs")
-        rt.forbid_autograd(self.parameters(), "VisualPacker_3d_phi_v3")
-        if self.training and self.resolution_attention.dropout.p > 0:
-            raise NotImplementedError(
-                "VisualPacker_3d_phi_v3 in .train() mode applies Dropout(p=0.1) inside resolution_attention "
-                "(spatial_pooling_projector.py:58-59); hsenet_b200 implements the eval-mode forward only")
+        if tr.needs_grad(self, visual_inputs):
+            raise RuntimeError("forward_into writes through raw pointers and is invisible to autograd; call the module "
+                               "(forward) when gradients are required")
+        self._check_dropout()
         if visual_inputs.dim() != 3 or visual_inputs.shape[1] != N_PATCH or visual_inputs.shape[2] != HIDDEN:
             raise ValueError(f"expected visual_inputs [B,2048,768], got {tuple(visual_inputs.shape)}")
         if visual_inputs.stride(2) != 1:
@@ -131,6 +179,8 @@ class VisualPacker_3d_phi_v3(nn.Module):
         return out
 
     def forward(self, visual_inputs):
+        if tr.needs_grad(self, visual_inputs):
+            return self._forward_train(visual_inputs)
         B = visual_inputs.shape[0]
         dt = self.output_dtype or rt.act_dtype()
         out = torch.empty(B, self.proj_out_num, self.out_dim, dtype=dt, device=visual_inputs.device)

@@ -22,6 +22,7 @@ import torch.nn as nn
 
 from . import _lib
 from . import runtime as rt
+from . import training as tr
 
 IMG_SIZE = (32, 256, 256)
 PATCH_SIZE = (4, 16, 16)
@@ -162,6 +163,7 @@ class _ViTBase(nn.Module):
         #: results are no longer bit-identical from run to run.  HSENET_LN_FOLD=1 or module.fold_layernorm = True.
         self.fold_layernorm = os.environ.get("HSENET_LN_FOLD", "0") == "1"
         self._cache = rt.WeightCache()
+        self._train_cache = rt.WeightCache()
         self._graphs = rt.GraphCache()
 
     # -- weights -> C struct ---------------------------------------------------------------------------------------
@@ -209,14 +211,68 @@ class _ViTBase(nn.Module):
             w.b_score = k(rt.f32(self.patch_score_proj.bias).reshape(-1))
         return {"struct": w, "blocks": blocks, "keep": keep}
 
+    def _build_train_payload(self, prec: str):
+        """Weights for the training entry points: the inference payload (LayerNorms as their own kernels) plus the
+        transposed matrices the input-gradient GEMMs multiply by (include/hsenet_b200.h, hsenet_vit_weights_t)."""
+        pl = self._build_payload(prec, False)
+        keep = pl["keep"]
+
+        def kt(w):
+            t = tr.transpose_weight(w, prec)
+            keep.append(t)
+            return t.data_ptr()
+
+        n = len(self.blocks)
+        bt = (_lib.BlockWeightsT * max(n, 1))()
+        for i, blk in enumerate(self.blocks):
+            bt[i].w_qkv_t = kt(blk.attn.qkv.weight)
+            bt[i].w_out_t = kt(blk.attn.out_proj.weight)
+            bt[i].w_fc1_t = kt(blk.mlp.linear1.weight)
+            bt[i].w_fc2_t = kt(blk.mlp.linear2.weight)
+        wt = _lib.VitWeightsT()
+        wt.blocks_host = C.cast(bt, C.c_void_p)
+        if self._stage == 2:
+            a = self.slice_guided_attention
+            wt.w_sq_t = kt(a.Wq.weight)
+            wt.w_so_t = kt(a.output_linear.weight)
+        pl["struct_t"] = wt
+        pl["blocks_t"] = bt
+        return pl
+
+    def disable_dropout(self):
+        """Set p = 0 on the Dropout members of the slice-guided attention (the training kernels do not apply dropout;
+        see hsenet_b200/training.py).  ViT_stage1 has none."""
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
+        return self
+
     def refresh_weights(self):
         """Drop the derived weight copies and captured graphs (call after an in-place ``param.data`` update, which the
         (data_ptr, _version) signature of the weight cache cannot see)."""
         self._cache.invalidate()
+        self._train_cache.invalidate()
         self._graphs.clear()
 
     def _run(self, x, image_2d):
+        if tr.needs_grad(self):
+            return self._run_train(x, image_2d)
         return self._finish(self._launch(x, image_2d))
+
+    def _run_train(self, x, image_2d):
+        """Forward under autograd: activation-taping kernels + hsenet_vit_backward."""
+        rt.require_cuda(x, "images")
+        rt.require_cuda(self.norm.weight, f"{type(self).__name__} parameters")
+        if x.dim() != 5 or tuple(x.shape[1:]) != (1,) + IMG_SIZE:
+            raise ValueError(f"expected images of shape [B,1,32,256,256], got {tuple(x.shape)}")
+        if self._stage == 2 and image_2d is None:
+            raise ValueError("ViT_stage2.forward needs image_2d [B,32,768]")
+        tokens, patch = tr.VitTrainFn.apply(self, x, image_2d, *self.parameters())
+        self.last_patch_tokens = patch
+        if self.output_dtype is not None and self.output_dtype != tokens.dtype:
+            tokens = tokens.to(self.output_dtype)
+            self.last_patch_tokens = patch.to(self.output_dtype)
+        return tokens, []
 
     def _launch(self, x, image_2d):
         """Enqueue the forward on the current stream.  Returns (tensors, static, act): with CUDA graphs the tensors are
@@ -355,7 +411,7 @@ class ViT_stage2(_ViTBase):
         if self.training and self.slice_guided_attention.dropout.p > 0:
             raise NotImplementedError(
                 "ViT_stage2 in .train() mode applies Dropout(p=0.1) inside slice_guided_attention (vit.py:46-47); "
-                "hsenet_b200 implements the eval-mode forward only -- call .eval()")
+                "the hsenet_b200 kernels do not apply dropout -- call .eval() or .disable_dropout() (p = 0)")
 
     def forward(self, x, image_2d, k=None, visual_encoder_2D=None, text_features=None, image_path=None):
         self._check_mode()

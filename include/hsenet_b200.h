@@ -221,6 +221,89 @@ int hsenet_crop_normalize_resize(const float* x, int d0, int d1, int d2, const f
 int hsenet_fold_layernorm(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
                           void* w_folded_bf16, float* colsum, float* bias_folded, hsenet_stream_t stream);
 
+/* ================================================================================================================
+ * Training path.  The reference trains both ViTs in CLIP stages 1-2
+ * (train/train_CLIP_stage1.py:231-257, train_CLIP_stage2.py:239-267) and the two packers in the VLM stage
+ * (train/train_VLM.py:406-414) through torch.autograd; here the façades wrap these entry points in
+ * torch.autograd.Function.  A training forward saves its activations on a caller-allocated TAPE; the backward
+ * consumes the tape and writes one fp32 gradient per parameter (pointers may be NULL to skip a gradient).
+ * Deterministic: every reduction has a fixed order, there are no atomics.
+ * Weight operands of the input-gradient GEMMs are the TRANSPOSED matrices ([in,out] row-major, activation dtype), which
+ * the façade derives once per weight update (hsenet_transpose_weight).
+ * ================================================================================================================ */
+typedef struct hsenet_block_weights_t {
+  const void* w_qkv_t; /* [768,2304]  attn.qkv.weight^T      */
+  const void* w_out_t; /* [768,768]   attn.out_proj.weight^T */
+  const void* w_fc1_t; /* [768,3072]  mlp.linear1.weight^T   */
+  const void* w_fc2_t; /* [3072,768]  mlp.linear2.weight^T   */
+} hsenet_block_weights_t;
+
+typedef struct hsenet_vit_weights_t {
+  const hsenet_block_weights_t* blocks_host; /* HOST array of num_layers entries */
+  const void* w_sq_t;                        /* stage 2: Wq.weight^T [768,768]            */
+  const void* w_so_t;                        /* stage 2: output_linear.weight^T [768,768] */
+} hsenet_vit_weights_t;
+
+typedef struct hsenet_block_grads {  /* fp32, shapes of the parameters; qkv has no bias */
+  float *w_qkv, *w_out, *b_out, *w_fc1, *b_fc1, *w_fc2, *b_fc2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+} hsenet_block_grads;
+
+typedef struct hsenet_vit_grads {
+  const hsenet_block_grads* blocks_host; /* HOST array of num_layers entries */
+  float *cls_token, *pos_embed, *w_patch, *b_patch, *norm_g, *norm_b;
+  /* stage 2 */
+  float *w_sq, *b_sq, *w_skv, *b_skv, *w_so, *b_so, *sn_g, *sn_b, *w_score, *b_score;
+} hsenet_vit_grads;
+
+typedef struct hsenet_packer_weights_t {
+  const void* w_q_t;  /* [768,768]       Wq.weight^T            */
+  const void* w_kv_t; /* [768,1536]      (Wk | Wv).weight^T     (only used when d_hr is requested) */
+  const void* w_o_t;  /* [768,768]       output_linear.weight^T */
+  const void* w_p0_t; /* [768,out_dim]   proj_mpls.0.weight^T   */
+  const void* w_p2_t; /* [out_dim,out_dim] proj_mpls.2.weight^T */
+} hsenet_packer_weights_t;
+
+typedef struct hsenet_packer_grads {
+  float *w_q, *b_q, *w_kv, *b_kv, *w_o, *b_o, *ln_g, *ln_b, *w_p0, *b_p0, *w_p2, *b_p2;
+} hsenet_packer_grads;
+
+/* out[cols,rows] = in[rows,cols]^T, fp32 in, activation dtype out (HSENET_DTYPE_BF16 / _F32). */
+int hsenet_transpose_weight(const float* in, int rows, int cols, void* out, int out_dtype, hsenet_stream_t stream);
+
+size_t hsenet_vit_tape_bytes(int B, int precision, int stage, int num_layers);
+size_t hsenet_vit_train_workspace_bytes(int B, int precision, int stage);
+/* Same results contract as hsenet_vit_forward (without hidden states); additionally fills `tape`.  GELU of the MLP is the
+ * exact erf form applied to the bf16-rounded pre-activation (the pre-activation is what the tape keeps). */
+int hsenet_vit_forward_train(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B,
+                             int precision, void* out_tokens, void* out_patch, float* scores_f32, void* tape,
+                             size_t tape_bytes, void* workspace, size_t workspace_bytes, hsenet_stream_t stream);
+/* d_tokens [B,2049,768] / d_patch [B,2048,768] in the activation dtype: gradients of the two outputs (either may be
+ * NULL).  images: the forward's input (the patch matrix is re-derived from it, not taped). */
+int hsenet_vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, const float* images, int B,
+                        int precision, const void* d_tokens, const void* d_patch, const void* tape, size_t tape_bytes,
+                        const hsenet_vit_grads* grads, void* workspace, size_t workspace_bytes,
+                        hsenet_stream_t stream);
+
+size_t hsenet_packer_tape_bytes(int B, int precision, int out_dim);
+size_t hsenet_packer_train_workspace_bytes(int B, int precision, int out_dim);
+/* out: [B,128,out_dim] contiguous in the activation dtype. */
+int hsenet_packer_forward_train(const hsenet_packer_weights* w, const void* hr, int B, int precision, void* out,
+                                void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
+                                hsenet_stream_t stream);
+/* d_out [B,128,out_dim] activation dtype; hr: the forward's input.  d_hr (optional): fp32 [B,2048,768] gradient of the
+ * tower features (needs wt->w_kv_t). */
+int hsenet_packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_t* wt, const void* hr, int B,
+                           int precision, const void* d_out, const void* tape, size_t tape_bytes,
+                           const hsenet_packer_grads* grads, float* d_hr, void* workspace, size_t workspace_bytes,
+                           hsenet_stream_t stream);
+
+/* Operator-level: backward of hsenet_self_attention.  lse / dvec: fp32 [B,12,ceil(S/128)*128]; lse comes from
+ * hsenet_self_attention_train. */
+int hsenet_self_attention_train(const void* qkv, void* out, float* lse, int B, int S, int precision,
+                                hsenet_stream_t stream);
+int hsenet_self_attention_backward(const void* qkv, const void* out, const void* d_out, const float* lse, float* dvec,
+                                   void* d_qkv, int B, int S, int precision, hsenet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -447,6 +447,56 @@ __global__ void __launch_bounds__(256) slice_extract_kernel(const float* __restr
   }
 }
 
+// 256 -> 224 (the reference's size, vit.py:529) is exactly 8 : 7.  With src = (8/7)(x + 0.5) - 0.5 the outputs 7k .. 7k+6 of a
+// row interpolate between inputs 8k+j and 8k+j+1 (the fractional parts 0.07 .. 0.93 never come near an integer, so float
+// rounding cannot move an index), i.e. each group of 7 outputs reads ONE aligned group of 8 inputs per source row:
+// a lane loads 2 x 2 float4 (a warp = the two full 1 KB source rows, perfectly coalesced) and produces 7 outputs with
+// compile-time register indices; the output row is staged in shared memory and stored as 128-bit words to the three
+// channel planes.  The generic kernel above issued 16 scalar loads per 4 outputs and was issue-bound (ncu: 67 % issue
+// slots, 44 % of the DRAM rate).  Weights are computed per x with the same fp32 expression, so results are bit-identical.
+template <typename OutT>
+__global__ void __launch_bounds__(256) slice_extract_224_kernel(const float* __restrict__ vol, OutT* __restrict__ out) {
+  __shared__ __align__(16) OutT stage[8][224];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.y;
+  const int y = blockIdx.x * 8 + warp;                 // 28 blocks x 8 rows = 224
+  const float* src = vol + static_cast<long>(slice) * (256 * 256);
+  const float sc = 256.0f / 224.0f;
+  float fy = sc * (y + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = y0 + (y0 < 255 ? 1 : 0);
+  const float ly = fy - y0, hy = 1.f - ly;
+  float a[8], b[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + y0 * 256 + lane * 8));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + y0 * 256 + lane * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(src + y1 * 256 + lane * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(src + y1 * 256 + lane * 8 + 4));
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int x = lane * 7 + j;
+    float fx = sc * (x + 0.5f) - 0.5f;
+    fx = fx < 0.f ? 0.f : fx;
+    const float lx = fx - static_cast<float>(lane * 8 + j), hx = 1.f - lx;      // xa == 8 * lane + j
+    const float r = hy * (hx * a[j] + lx * a[j + 1]) + ly * (hx * b[j] + lx * b[j + 1]);
+    stage[warp][x] = static_cast<OutT>(r);
+  }
+  __syncwarp();
+  constexpr int kVecs = 224 * static_cast<int>(sizeof(OutT)) / 16;      // 28 (bf16) or 56 (fp32) 16-byte words per row
+  const long plane = 224L * 224;
+  OutT* o = out + static_cast<long>(slice) * 3 * plane + static_cast<long>(y) * 224;
+  for (int v = lane; v < kVecs; v += 32) {
+    const uint4 w = reinterpret_cast<const uint4*>(&stage[warp][0])[v];
+    reinterpret_cast<uint4*>(o)[v] = w;
+    reinterpret_cast<uint4*>(o + plane)[v] = w;
+    reinterpret_cast<uint4*>(o + 2 * plane)[v] = w;
+  }
+}
+
 __global__ void patch_map_kernel(int32_t* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kNPatch * kPatchDim) out[i] = patch_voxel(i / kPatchDim, i % kPatchDim);
@@ -654,6 +704,11 @@ int slice_extract(const float* vol, OutT* out, int B, int oh, int ow, cudaStream
   const float sy = 256.0f / static_cast<float>(oh);
   const float sx = 256.0f / static_cast<float>(ow);
   ProfScope prof(PROF_SLICE_EXTRACT, 0.0, double(B) * 32.0 * (256.0 * 256.0 * 4.0 + 3.0 * oh * ow * sizeof(OutT)), stream);
+  if (oh == 224 && ow == 224 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && aligned16(vol)) {
+    slice_extract_224_kernel<OutT><<<dim3(28, B * 32), 256, 0, stream>>>(vol, out);
+    count_launch();
+    return launch_status();
+  }
   slice_extract_kernel<OutT><<<dim3((oh + 3) / 4, B * 32), 256, 0, stream>>>(vol, out, oh, ow, sy, sx);
   count_launch();
   return launch_status();

@@ -91,11 +91,13 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
 
 
 def forbid_autograd(params: Iterable[torch.Tensor], what: str) -> None:
-    """Forward-only in this round (SURVEY.md section 8 row f-1 is the backward)."""
+    """Guard of the inference-only launch paths (raw-pointer writes, graph replays): they are invisible to autograd, so
+    reaching one with trainable parameters under grad mode is a bug -- the modules route such calls to the training path
+    (hsenet_b200/training.py) before getting here."""
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         raise NotImplementedError(
-            f"hsenet_b200.{what}: backward is not implemented yet; run under torch.no_grad() / inference_mode() "
-            "or freeze the module with requires_grad_(False).")
+            f"hsenet_b200.{what}: this launch path does not record an autograd graph; call the module's forward "
+            "(training path) or run under torch.no_grad().")
 
 
 # ---- workspaces: one growing buffer per (device, stream, tag) -----------------------------------------------------

@@ -442,8 +442,8 @@ class ViT3DTower_dual_encoders(nn.Module):
         if self.select_feature not in ("patch", "cls_patch"):
             raise ValueError(f"Unexpected select feature: {self.select_feature}")
         feats = []
-        if t == "dual_vits" and self.concurrent_towers and images.is_cuda:
-            return self._forward_concurrent(images, images_2d)
+        if t == "dual_vits" and self.concurrent_towers and images.is_cuda and not tr.needs_grad(self):
+            return self._forward_concurrent(images, images_2d)     # frozen towers (VLM stage): graph replays on two streams
         # the reference always runs both encoders (vit.py:928-929); skipping the unused one changes no result
         if t in ("dual_vits", "3d_vit"):
             tok, _ = self.vision_tower_stage1(images)

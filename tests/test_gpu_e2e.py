@@ -161,8 +161,13 @@ def test_no_cpu_path_and_errors(cuda):
     m = m.to(cuda)
     with torch.no_grad(), pytest.raises(ValueError):
         m(torch.zeros(1, 1, 16, 256, 256, device=cuda))
+    # grad enabled + trainable parameters: the training path (row f-1) -- never a silent detach
+    y, _ = m(torch.zeros(1, 1, 32, 256, 256, device=cuda))
+    assert y.requires_grad and y.grad_fn is not None
+    # train-mode dropout of the slice-guided attention is rejected, not ignored (hsenet_b200/training.py)
+    m2 = _build(H.ViT_stage2, 1).to(cuda).train()
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 1, 32, 256, 256, device=cuda))   # grad enabled + trainable params: no silent detach
+        m2(torch.zeros(1, 1, 32, 256, 256, device=cuda), torch.zeros(1, 32, 768, device=cuda))
 
 
 def test_splice_into_llm_embeddings(cuda):

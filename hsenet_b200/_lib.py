@@ -16,6 +16,7 @@ ERR_SHAPE, ERR_ALIGN, ERR_CUDA, ERR_ARG, ERR_DRIVER = -1, -2, -3, -4, -5
 PREC_BF16, PREC_FP32_VERIFY = 0, 1
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 PROFILE_CLASSES = 10      # HSENET_PROFILE_CLASSES
+VIT_PATCH_DONE = 1        # HSENET_VIT_PATCH_DONE
 
 vp = C.c_void_p
 
@@ -29,7 +30,8 @@ class BlockWeights(C.Structure):
 class VitWeights(C.Structure):
     _fields_ = [("stage", C.c_int32), ("num_layers", C.c_int32)] + [
         (n, vp) for n in ("cls_token", "pos_embed", "w_patch", "b_patch", "blocks_host", "norm_g", "norm_b",
-                          "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score")]
+                          "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score",
+                          "w_patch_f32")]
 
 
 class PackerWeights(C.Structure):
@@ -52,7 +54,8 @@ class BlockGrads(C.Structure):
 
 class VitGrads(C.Structure):
     _fields_ = [(n, vp) for n in ("blocks_host", "cls_token", "pos_embed", "w_patch", "b_patch", "norm_g", "norm_b",
-                                  "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score")]
+                                  "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score",
+                          "w_patch_f32")]
 
 
 class PackerWeightsT(C.Structure):
@@ -73,7 +76,9 @@ SIGNATURES = {
                                       C.POINTER(C.c_uint64)]),
     "hsenet_vit_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hsenet_vit_forward": (C.c_int, [C.POINTER(VitWeights), vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp,
-                                     C.c_size_t, vp]),
+                                     C.c_size_t, C.c_int, vp]),
+    "hsenet_patch_embed_dual": (C.c_int, [C.POINTER(VitWeights), C.POINTER(VitWeights), vp, vp, C.c_int, vp, C.c_size_t,
+                                          vp, C.c_size_t, vp]),
     "hsenet_packer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hsenet_packer_forward": (C.c_int, [C.POINTER(PackerWeights), vp, C.c_int, C.c_int, vp, C.c_int, C.c_int,
                                         C.c_int, vp, C.c_size_t, vp]),

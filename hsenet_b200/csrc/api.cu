@@ -132,40 +132,57 @@ struct VitWs {
   }
 };
 
+// stage 2 keeps the fp32 patch embedding behind the (former) patch-matrix region of H
+template <typename T>
+float* stage2_xp(const VitWs<T>& ws, int Mp) {
+  return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.H) + align_up(static_cast<size_t>(Mp) * kPatchDim * sizeof(T)));
+}
+// Epilogue of the patch-embedding GEMM of one tower: bias + positional embedding; stage 1 writes the rows behind the cls row
+// of the residual stream (fuses torch.cat, vit.py:459-461), stage 2 into the fp32 + activation-dtype patch buffers.
+template <typename T>
+GemmEpilogue patch_epilogue(const hsenet_vit_weights* w, const VitWs<T>& ws, int B) {
+  GemmEpilogue ep;
+  ep.bias = w->b_patch;
+  ep.row_add = w->pos_embed;
+  ep.rows_per_group = kNPatch;
+  if (w->stage == 1) {
+    ep.group_stride = kSeq; ep.group_offset = 1;
+    ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
+  } else {
+    ep.group_stride = kNPatch; ep.group_offset = 0;
+    ep.out_f32 = stage2_xp<T>(ws, B * kNPatch); ep.ld_f32 = kHidden;
+    set_act_out(ep, ws.XN, kHidden);
+  }
+  return ep;
+}
+
 template <typename T>
 int vit_forward(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B, T* out_tokens,
-                T* out_patch, float* hidden, float* scores, void* workspace, size_t workspace_bytes,
+                T* out_patch, float* hidden, float* scores, void* workspace, size_t workspace_bytes, int flags,
                 cudaStream_t st) {
   VitWs<T> ws(workspace, B);
   if (workspace_bytes < ws.total) return HS_ERR_ARG;
   const int M = B * kSeq, Mp = B * kNPatch;
   T* P = ws.H;                                                            // im2col patches [Mp,1024]
 
-  // K1: patch embedding = im2col + GEMM with fused bias + positional embedding (+ cls-offset row remap)
-  HS_TRY(im2col_patches<T>(images, B, P, st));
-  if (w->stage == 1) {
-    GemmEpilogue ep;
-    ep.bias = w->b_patch;
-    ep.row_add = w->pos_embed;
-    ep.rows_per_group = kNPatch; ep.group_stride = kSeq; ep.group_offset = 1;
-    ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
-    HS_TRY(Prec<T>::gemm(P, kPatchDim, w->w_patch, kPatchDim, Mp, kHidden, kPatchDim, ep, st));
-  } else {
+  // K1: patch embedding with fused bias + positional embedding (+ cls-offset row remap).  bf16 mode: implicit-im2col
+  // tf32 GEMM straight from the volume (patch_embed_tcgen05.cu) unless the caller already ran it for both towers at once
+  // (hsenet_patch_embed_dual, flags & 1); verification mode: explicit im2col + fp32 GEMM.
+  const GemmEpilogue pe = patch_epilogue<T>(w, ws, B);
+  if (!(flags & HSENET_VIT_PATCH_DONE)) {
+    if (std::is_same<T, __nv_bfloat16>::value && w->w_patch_f32 != nullptr) {
+      HS_TRY(patch_embed_tf32(images, w->w_patch_f32, B, 1, pe, pe, st));
+    } else {
+      HS_TRY(im2col_patches<T>(images, B, P, st));
+      HS_TRY(Prec<T>::gemm(P, kPatchDim, w->w_patch, kPatchDim, Mp, kHidden, kPatchDim, pe, st));
+    }
+  }
+  if (w->stage == 2) {
     if (images_2d == nullptr) return HS_ERR_ARG;
-    float* XP = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.H) +
-                                         align_up(static_cast<size_t>(Mp) * kPatchDim * sizeof(T)));
+    float* XP = stage2_xp<T>(ws, Mp);
     T* XPa = ws.XN;
     float* Q = reinterpret_cast<float*>(ws.QKV);
     T* O = ws.ATT;
-    {
-      GemmEpilogue ep;
-      ep.bias = w->b_patch;
-      ep.row_add = w->pos_embed;
-      ep.rows_per_group = kNPatch; ep.group_stride = kNPatch; ep.group_offset = 0;
-      ep.out_f32 = XP; ep.ld_f32 = kHidden;
-      set_act_out(ep, XPa, kHidden);
-      HS_TRY(Prec<T>::gemm(P, kPatchDim, w->w_patch, kPatchDim, Mp, kHidden, kPatchDim, ep, st));
-    }
     // K10: regular_attention(x, slices, slices)  (vit.py:50-64)
     HS_TRY(cast_rows<T>(images_2d, ws.S16, static_cast<long>(B) * kNSlice * kHidden, st));
     {
@@ -398,18 +415,32 @@ size_t hsenet_vit_workspace_bytes(int B, int precision, int stage) {
 
 int hsenet_vit_forward(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B,
                        int precision, void* out_tokens, void* out_patch, float* hidden_f32, float* scores_f32,
-                       void* workspace, size_t workspace_bytes, hsenet_stream_t stream) {
+                       void* workspace, size_t workspace_bytes, int flags, hsenet_stream_t stream) {
   if (w == nullptr || images == nullptr || workspace == nullptr || w->blocks_host == nullptr) return HSENET_ERR_ARG;
   if (B <= 0 || w->num_layers < 0 || (w->stage != 1 && w->stage != 2)) return HSENET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == HSENET_PREC_BF16)
     return vit_forward<__nv_bfloat16>(w, images, images_2d, B, static_cast<__nv_bfloat16*>(out_tokens),
                                       static_cast<__nv_bfloat16*>(out_patch), hidden_f32, scores_f32, workspace,
-                                      workspace_bytes, st);
+                                      workspace_bytes, flags, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return vit_forward<float>(w, images, images_2d, B, static_cast<float*>(out_tokens),
-                              static_cast<float*>(out_patch), hidden_f32, scores_f32, workspace, workspace_bytes, st);
+                              static_cast<float*>(out_patch), hidden_f32, scores_f32, workspace, workspace_bytes,
+                              flags & ~HSENET_VIT_PATCH_DONE, st);
   return HSENET_ERR_ARG;
+}
+
+int hsenet_patch_embed_dual(const hsenet_vit_weights* w1, const hsenet_vit_weights* w2, const float* w_stack_f32,
+                            const float* images, int B, void* workspace1, size_t workspace1_bytes, void* workspace2,
+                            size_t workspace2_bytes, hsenet_stream_t stream) {
+  if (w1 == nullptr || w2 == nullptr || w_stack_f32 == nullptr || images == nullptr || workspace1 == nullptr ||
+      workspace2 == nullptr || B <= 0)
+    return HSENET_ERR_ARG;
+  if (w1->stage != 1 || w2->stage != 2) return HSENET_ERR_ARG;
+  VitWs<__nv_bfloat16> ws1(workspace1, B), ws2(workspace2, B);
+  if (workspace1_bytes < ws1.total || workspace2_bytes < ws2.total) return HSENET_ERR_ARG;
+  return patch_embed_tf32(images, w_stack_f32, B, 2, patch_epilogue<__nv_bfloat16>(w1, ws1, B),
+                          patch_epilogue<__nv_bfloat16>(w2, ws2, B), static_cast<cudaStream_t>(stream));
 }
 
 size_t hsenet_packer_workspace_bytes(int B, int precision, int out_dim) {

@@ -134,23 +134,28 @@ __global__ void __launch_bounds__(256) hu_transpose_kernel(const float* __restri
 // the z / a source indices and weights are block-uniform and the only per-thread index math is one axis.  (The first
 // version decomposed a flat 64-bit index with three 64-bit divisions per voxel: ncu showed it issue-bound, 72 % issue
 // slots at 19 % of the DRAM rate.)
+constexpr int kResZ = 8;      // output slices per block: amortises block launch and the per-row index math
 __global__ void __launch_bounds__(128) resample_kernel(const float* __restrict__ x, int d0, int d1, int d2,
                                                        float* __restrict__ out, int o0, int o1, int o2, float s0,
                                                        float s1, float s2) {
-  const int z = blockIdx.z, a = blockIdx.y;
+  const int a = blockIdx.y;
   const int b = blockIdx.x * 128 + threadIdx.x;
   if (b >= o2) return;
-  const Axis t = src_index(z, d0, s0), h = src_index(a, d1, s1), w = src_index(b, d2, s2);
-  const float* p00 = x + (static_cast<long>(t.i0) * d1 + h.i0) * d2;
-  const float* p01 = x + (static_cast<long>(t.i0) * d1 + h.i1) * d2;
-  const float* p10 = x + (static_cast<long>(t.i1) * d1 + h.i0) * d2;
-  const float* p11 = x + (static_cast<long>(t.i1) * d1 + h.i1) * d2;
-  // same nesting as trilinear(): t(h(w))
-  const float v = t.l0 * (h.l0 * (w.l0 * __ldg(p00 + w.i0) + w.l1 * __ldg(p00 + w.i1)) +
-                          h.l1 * (w.l0 * __ldg(p01 + w.i0) + w.l1 * __ldg(p01 + w.i1))) +
-                  t.l1 * (h.l0 * (w.l0 * __ldg(p10 + w.i0) + w.l1 * __ldg(p10 + w.i1)) +
-                          h.l1 * (w.l0 * __ldg(p11 + w.i0) + w.l1 * __ldg(p11 + w.i1)));
-  out[(static_cast<long>(z) * o1 + a) * o2 + b] = v;
+  const Axis h = src_index(a, d1, s1), w = src_index(b, d2, s2);
+  const int z_end = min((blockIdx.z + 1) * kResZ, o0);
+  for (int z = blockIdx.z * kResZ; z < z_end; ++z) {
+    const Axis t = src_index(z, d0, s0);
+    const float* p00 = x + (static_cast<long>(t.i0) * d1 + h.i0) * d2;
+    const float* p01 = x + (static_cast<long>(t.i0) * d1 + h.i1) * d2;
+    const float* p10 = x + (static_cast<long>(t.i1) * d1 + h.i0) * d2;
+    const float* p11 = x + (static_cast<long>(t.i1) * d1 + h.i1) * d2;
+    // same nesting as trilinear(): t(h(w))
+    const float v = t.l0 * (h.l0 * (w.l0 * __ldg(p00 + w.i0) + w.l1 * __ldg(p00 + w.i1)) +
+                            h.l1 * (w.l0 * __ldg(p01 + w.i0) + w.l1 * __ldg(p01 + w.i1))) +
+                    t.l1 * (h.l0 * (w.l0 * __ldg(p10 + w.i0) + w.l1 * __ldg(p10 + w.i1)) +
+                            h.l1 * (w.l0 * __ldg(p11 + w.i0) + w.l1 * __ldg(p11 + w.i1)));
+    out[(static_cast<long>(z) * o1 + a) * o2 + b] = v;
+  }
 }
 
 // order-preserving float <-> int so that integer atomics give an exact float min / max
@@ -282,8 +287,8 @@ int hu_resample(const float* raw, int n0, int n1, int n2, float slope, float int
       const dim3 tg(static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>((n2 + 31) / 32));
       hu_transpose_kernel<<<tg, 256, 0, st>>>(raw, rows, n2, slope, intercept, hu_min, hu_max, scratch);
     }
-    if (o0 > 65535 || o1 > 65535) return HS_ERR_SHAPE;
-    resample_kernel<<<dim3((o2 + 127) / 128, o1, o0), 128, 0, st>>>(scratch, n2, n0, n1, out, o0, o1, o2, s0, s1, s2);
+    if (o1 > 65535) return HS_ERR_SHAPE;
+    resample_kernel<<<dim3((o2 + 127) / 128, o1, (o0 + kResZ - 1) / kResZ), 128, 0, st>>>(scratch, n2, n0, n1, out, o0, o1, o2, s0, s1, s2);
     count_launch();
     count_launch();
     return launch_ok();

@@ -93,6 +93,11 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
 int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
              cudaStream_t stream);
 
+// Implicit-im2col patch embedding of one or both towers (patch_embed_tcgen05.cu): tf32 tcgen05 GEMM whose A tiles are
+// 5-D TMA boxes of the fp32 volume; w_stack fp32 [n_towers*768,1024]; ep0 / ep1 = the towers' epilogues.
+int patch_embed_tf32(const float* images, const float* w_stack, int B, int n_towers, const GemmEpilogue& ep0,
+                     const GemmEpilogue& ep1, cudaStream_t stream);
+
 // ---- self attention over the 3D token sequence (MONAI SABlock core) --------------------------------------------
 // qkv [B*S, 2304] with feature order (qkv, head, d); out [B*S, 768] heads concatenated.
 // lse (optional, training forward): [B, 12, S_pad] fp32 with S_pad = ceil(S/128)*128, log2-domain log-sum-exp of the scaled

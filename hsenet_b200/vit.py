@@ -198,6 +198,8 @@ class _ViTBase(nn.Module):
         w.pos_embed = k(rt.f32(self.patch_embedding.position_embeddings).reshape(N_PATCH, HIDDEN))
         lin = self.patch_embedding.patch_embeddings[1]
         w.w_patch = k(cw(lin.weight)); w.b_patch = k(rt.f32(lin.bias))
+        if prec == "bf16" and os.environ.get("HSENET_PATCH_IM2COL", "0") != "1":
+            w.w_patch_f32 = k(rt.f32(lin.weight))          # implicit-im2col tf32 patch embedding (A/B: HSENET_PATCH_IM2COL=1)
         w.blocks_host = C.cast(blocks, C.c_void_p)
         w.norm_g = k(rt.f32(self.norm.weight)); w.norm_b = k(rt.f32(self.norm.bias))
         if self._stage == 2:
@@ -274,9 +276,30 @@ class _ViTBase(nn.Module):
             self.last_patch_tokens = patch.to(self.output_dtype)
         return tokens, []
 
-    def _launch(self, x, image_2d):
+    def _workspace(self, B, prec):
+        """This tower's scratch buffer for the CURRENT stream (one per (device, stream): the dual tower runs its two
+        encoders on two streams)."""
+        dev = self.norm.weight.device
+        nbytes = _lib.load().hsenet_vit_workspace_bytes(B, rt.precision_code(prec), self._stage)
+        return rt.workspace(dev, nbytes, f"vit_stage{self._stage}")
+
+    def _inference_payload(self, prec):
+        fold = bool(self.fold_layernorm) and prec == "bf16"
+        with torch.cuda.device(self.norm.weight.device):
+            return self._cache.get(self.parameters(), prec + ("+ln" if fold else ""),
+                                   lambda key: self._build_payload(prec, fold))
+
+    def _launch(self, x, image_2d, patch_done=False):
         """Enqueue the forward on the current stream.  Returns (tensors, static, act): with CUDA graphs the tensors are
         the graph's static output buffers (``static`` True) and must be copied before the next call -- ``_finish`` does."""
+        return self._replay(self._prepare(x, image_2d, patch_done))
+
+    def _prepare(self, x, image_2d, patch_done=False):
+        """Validate the call and make sure its CUDA graph exists (capturing it on first use) WITHOUT running the forward.
+        ``patch_done``: the patch embedding of this call is written into this tower's workspace by the caller
+        (hsenet_patch_embed_dual, one kernel for both encoders of the dual tower) between ``_prepare`` and ``_replay``;
+        the captured forward then starts after it.  Capturing needs a warm-up launch that consumes the workspace, which is
+        why preparation and replay are separate steps."""
         rt.require_cuda(x, "images")
         rt.require_cuda(self.norm.weight, f"{type(self).__name__} parameters")
         rt.forbid_autograd(self.parameters(), type(self).__name__)
@@ -286,9 +309,7 @@ class _ViTBase(nn.Module):
         B = x.shape[0]
         prec = rt.get_precision()
         fold = bool(self.fold_layernorm) and prec == "bf16"
-        with torch.cuda.device(dev):
-            payload = self._cache.get(self.parameters(), prec + ("+ln" if fold else ""),
-                                      lambda key: self._build_payload(prec, fold))
+        payload = self._inference_payload(prec)
         lib = _lib.load()
         act = rt.act_dtype(prec)
         xin = x.detach().float().contiguous()                 # reference clones its input (vit.py:455)
@@ -301,8 +322,9 @@ class _ViTBase(nn.Module):
                 raise ValueError(f"image_2d must reshape to [B,32,768], got {tuple(image_2d.shape)}")
         want_hidden = self.return_hidden_states and len(self.blocks) > 0
         pc = rt.precision_code(prec)
-        nbytes = lib.hsenet_vit_workspace_bytes(B, pc, self._stage)
-        ws = rt.workspace(dev, nbytes, f"vit_stage{self._stage}")   # one per stage: the dual tower runs them concurrently
+        with torch.cuda.device(dev):
+            ws = self._workspace(B, prec)                      # one per stage and stream: the dual tower runs them concurrently
+        flags = _lib.VIT_PATCH_DONE if patch_done else 0
 
         def alloc_outputs():
             tok = torch.empty(B, SEQ, HIDDEN, dtype=act, device=dev)
@@ -313,39 +335,49 @@ class _ViTBase(nn.Module):
 
         def launch(xi, si, tok, pat, hid, sc):
             rc = lib.hsenet_vit_forward(C.byref(payload["struct"]), xi.data_ptr(), rt.ptr(si), B, pc, tok.data_ptr(),
-                                        pat.data_ptr(), rt.ptr(hid), rt.ptr(sc), ws.data_ptr(), ws.numel(),
+                                        pat.data_ptr(), rt.ptr(hid), rt.ptr(sc), ws.data_ptr(), ws.numel(), flags,
                                         rt.stream_ptr(dev))
             _lib.check(rc, f"vit_forward(stage={self._stage})")
 
+        call = dict(dev=dev, act=act, xin=xin, s2d=s2d, patch_done=patch_done, launch=launch, alloc=alloc_outputs, ent=None)
+        if not self.use_cuda_graph:
+            return call
         with torch.cuda.device(dev):
-            if self.use_cuda_graph:
-                key = (B, prec, fold, dev.index, want_hidden, int(torch.cuda.current_stream(dev).cuda_stream))
-                ent = self._graphs.get(key, self._cache.generation, ws.data_ptr())
-                if ent is None:
-                    xi = torch.empty(B, 1, *IMG_SIZE, dtype=torch.float32, device=dev)
-                    si = torch.empty(B, 32, HIDDEN, dtype=torch.float32, device=dev) if self._stage == 2 else None
-                    outs = alloc_outputs()
-                    xi.copy_(xin)
-                    if si is not None:
-                        si.copy_(s2d)
-                    launch(xi, si, *outs)                      # warm-up outside capture (one-time attribute setup)
-                    torch.cuda.current_stream(dev).synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    n0 = lib.hsenet_launch_count()
-                    with torch.cuda.graph(g):
-                        launch(xi, si, *outs)
-                    ent = self._graphs.put(key, self._cache.generation, ws.data_ptr(),
-                                           dict(graph=g, xi=xi, si=si, outs=outs,
-                                                kernels=int(lib.hsenet_launch_count() - n0)), keep=(payload, ws))
-                ent["xi"].copy_(xin)
-                if ent["si"] is not None:
-                    ent["si"].copy_(s2d)
-                ent["graph"].replay()
-                rt.note_graph_kernels(ent["kernels"])
-                return ent["outs"], True, act
-            outs = alloc_outputs()
-            launch(xin, s2d, *outs)
-            return outs, False, act
+            key = (B, prec, fold, dev.index, want_hidden, flags, int(torch.cuda.current_stream(dev).cuda_stream))
+            ent = self._graphs.get(key, self._cache.generation, ws.data_ptr())
+            if ent is None:
+                xi = torch.empty(B, 1, *IMG_SIZE, dtype=torch.float32, device=dev)
+                si = torch.empty(B, 32, HIDDEN, dtype=torch.float32, device=dev) if self._stage == 2 else None
+                outs = alloc_outputs()
+                xi.copy_(xin)
+                if si is not None:
+                    si.copy_(s2d)
+                launch(xi, si, *outs)                      # warm-up outside capture (one-time attribute setup)
+                torch.cuda.current_stream(dev).synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = lib.hsenet_launch_count()
+                with torch.cuda.graph(g):
+                    launch(xi, si, *outs)
+                ent = self._graphs.put(key, self._cache.generation, ws.data_ptr(),
+                                       dict(graph=g, xi=xi, si=si, outs=outs,
+                                            kernels=int(lib.hsenet_launch_count() - n0)), keep=(payload, ws))
+        call["ent"] = ent
+        return call
+
+    def _replay(self, call):
+        dev, ent = call["dev"], call["ent"]
+        with torch.cuda.device(dev):
+            if ent is None:                                    # direct launches
+                outs = call["alloc"]()
+                call["launch"](call["xin"], call["s2d"], *outs)
+                return outs, False, call["act"]
+            if not call["patch_done"]:                         # the graph only reads the volume in its patch embedding
+                ent["xi"].copy_(call["xin"])
+            if ent["si"] is not None:
+                ent["si"].copy_(call["s2d"])
+            ent["graph"].replay()
+            rt.note_graph_kernels(ent["kernels"])
+            return ent["outs"], True, call["act"]
 
     def _finish(self, launched):
         outs, static, act = launched
@@ -436,6 +468,9 @@ class ViT3DTower_dual_encoders(nn.Module):
         #: run the two (independent) encoders on two streams so that the partial last wave of every kernel of
         #: one encoder is filled by CTAs of the other (5.5 waves of attention CTAs, 2.6 waves of fc2 tiles at B = 8)
         self.concurrent_towers = os.environ.get("HSENET_CONCURRENT_TOWERS", "1") != "0"
+        #: one patch-embedding kernel for both encoders (hsenet_patch_embed_dual); HSENET_SHARED_PATCH=0 for A/B runs
+        self.shared_patch_embedding = os.environ.get("HSENET_SHARED_PATCH", "1") != "0"
+        self._stack_cache = rt.WeightCache()
 
     def forward(self, images, images_2d):
         t = self.remain_2d3d_ViT_type
@@ -469,11 +504,36 @@ class ViT3DTower_dual_encoders(nn.Module):
         dev = images.device
         cur = torch.cuda.current_stream(dev)
         side = rt.side_stream(dev)
-        side.wait_stream(cur)                       # images / weights produced on the caller's stream
-        with torch.cuda.stream(side):
-            l1 = t1._launch(images, None)           # graph replay into its static buffers
         t2._check_mode()
-        l2 = t2._launch(images, images_2d)
+        # One implicit-im2col GEMM writes the patch embeddings of BOTH encoders (they read the same volume, vit.py:928-929):
+        # N = 1536 over the stacked fp32 projections, results straight into the two workspaces (bf16 precision only).
+        dual = self.shared_patch_embedding and rt.get_precision() == "bf16" and \
+            tuple(images.shape[1:]) == (1,) + IMG_SIZE
+        # graphs first (a capture's warm-up launch consumes the workspace), then the shared patch embedding, then the replays
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            c1 = t1._prepare(images, None, patch_done=dual)
+        c2 = t2._prepare(images, images_2d, patch_done=dual)
+        cur.wait_stream(side)
+        if dual:
+            B = images.shape[0]
+            with torch.cuda.device(dev):
+                with torch.cuda.stream(side):
+                    ws1 = t1._workspace(B, "bf16")             # tower 1 runs on the side stream: its workspace lives there
+                ws2 = t2._workspace(B, "bf16")
+                p1, p2 = t1._inference_payload("bf16"), t2._inference_payload("bf16")
+                lin1, lin2 = t1.patch_embedding.patch_embeddings[1], t2.patch_embedding.patch_embeddings[1]
+                wst = self._stack_cache.get([lin1.weight, lin2.weight], "f32", lambda key: torch.cat(
+                    [rt.f32(lin1.weight), rt.f32(lin2.weight)], 0).contiguous())
+                xin = images.detach().float().contiguous()
+                rc = _lib.load().hsenet_patch_embed_dual(C.byref(p1["struct"]), C.byref(p2["struct"]), wst.data_ptr(),
+                                                         xin.data_ptr(), B, ws1.data_ptr(), ws1.numel(), ws2.data_ptr(),
+                                                         ws2.numel(), rt.stream_ptr(dev))
+            _lib.check(rc, "patch_embed_dual")
+        side.wait_stream(cur)                       # images / weights / patch embeddings produced on the caller's stream
+        with torch.cuda.stream(side):
+            l1 = t1._replay(c1)                     # graph replay into its static buffers
+        l2 = t2._replay(c2)
         cur.wait_stream(side)
         # every output tensor is allocated (cloned) on the caller's stream, after the join: allocating them on the side
         # stream and handing them over with record_stream made the caching allocator wait on cross-stream events or fall

@@ -97,7 +97,15 @@ typedef struct hsenet_vit_weights {
   const float* sn_b;
   const float* w_score; /* patch_score_proj.weight [768] */
   const float* b_score; /* patch_score_proj.bias   [1]   */
+  /* Optional: the fp32 patch projection [768,1024].  When set (bf16 precision) the patch embedding runs as an
+   * implicit-im2col tf32 tcgen05 GEMM fed by 5-D TMA boxes of the volume (no patch matrix is materialised); when NULL
+   * it runs as im2col + GEMM on w_patch. */
+  const float* w_patch_f32;
 } hsenet_vit_weights;
+
+/* hsenet_vit_forward flags */
+#define HSENET_VIT_PATCH_DONE 1 /* the patch embedding of this call was already written into the workspace by
+                                   hsenet_patch_embed_dual (bf16 precision only) */
 
 /* VisualPacker_3d_phi_v3 (spatial_pooling_projector.py:121-153). */
 typedef struct hsenet_packer_weights {
@@ -144,13 +152,21 @@ int hsenet_profile_stop(double* ms, double* flops, double* bytes, uint64_t* laun
 size_t hsenet_vit_workspace_bytes(int B, int precision, int stage);
 int hsenet_vit_forward(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B,
                        int precision, void* out_tokens, void* out_patch, float* hidden_f32, float* scores_f32,
-                       void* workspace, size_t workspace_bytes, hsenet_stream_t stream);
+                       void* workspace, size_t workspace_bytes, int flags, hsenet_stream_t stream);
 
 /* Replaces VisualPacker_3d_phi_v3.forward (spatial_pooling_projector.py:138-146) and the torch.cat of
  * LamedMetaForCausalLM.encode_images (lamed_arch.py:132): writes packed token n of batch b to
  *   out[(b * out_tokens_per_batch + token_offset + n) * out_dim + :],  n in [0,128).
  *   hr   act [B,2048,768] contiguous (tower features without cls);  out_dtype HSENET_DTYPE_* of `out`
  *   (BF16 mode: BF16 or F32; FP32_VERIFY: F32). */
+/* Patch embedding of ViT_stage1 AND ViT_stage2 in one launch (both read the same volume; vit.py:928-929 runs them on the
+ * same `images`): implicit-im2col tf32 GEMM over the stacked fp32 patch projections w_stack_f32 [1536,1024] (stage 1
+ * rows first), results written where hsenet_vit_forward(..., flags = HSENET_VIT_PATCH_DONE) of each tower expects them
+ * inside its own workspace.  bf16 precision only. */
+int hsenet_patch_embed_dual(const hsenet_vit_weights* w1, const hsenet_vit_weights* w2, const float* w_stack_f32,
+                            const float* images, int B, void* workspace1, size_t workspace1_bytes, void* workspace2,
+                            size_t workspace2_bytes, hsenet_stream_t stream);
+
 size_t hsenet_packer_workspace_bytes(int B, int precision, int out_dim);
 int hsenet_packer_forward(const hsenet_packer_weights* w, const void* hr, int B, int precision, void* out,
                           int out_dtype, int out_tokens_per_batch, int token_offset, void* workspace,

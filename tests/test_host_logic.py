@@ -204,6 +204,7 @@ def test_dual_tower_two_stream_path_plumbing(monkeypatch):
     import hsenet_b200 as H
     from hsenet_b200 import vit
     tw = H.ViT3DTower_dual_encoders(H.VisionConfig()).eval()
+    tw.shared_patch_embedding = False        # the shared patch-embedding kernel needs a device; this test is host plumbing
     log = []
 
     class FakeStream:
@@ -228,18 +229,26 @@ def test_dual_tower_two_stream_path_plumbing(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: cur)
     monkeypatch.setattr(torch.cuda, "stream", fake_stream_ctx)
     for t in (tw.vision_tower_stage1, tw.vision_tower_stage2):
-        def launch(x, s, _t=t):
-            log.append(("launch", _t._stage, active[-1], s is not None))
+        def prepare(x, s, patch_done=False, _t=t):
+            log.append(("prepare", _t._stage, active[-1], s is not None))
+            return {"stage": _t._stage}
+
+        def replay(call, _t=t):
+            log.append(("replay", call["stage"], active[-1]))
             return (torch.zeros(1, 2049, 768), torch.zeros(1, 2048, 768), None, None), True, torch.float32
 
         def finish(launched, _t=t, _orig=t._finish):
             log.append(("finish", _t._stage, active[-1]))
             return _orig(launched)
-        monkeypatch.setattr(t, "_launch", launch)
+        monkeypatch.setattr(t, "_prepare", prepare)
+        monkeypatch.setattr(t, "_replay", replay)
         monkeypatch.setattr(t, "_finish", finish)
     f1, f2 = tw._forward_concurrent(torch.zeros(1, 1, 32, 256, 256), torch.zeros(1, 32, 768))
     assert f1.shape == f2.shape == (1, 2048, 768)
-    assert log == [("wait", "side", "cur"), ("launch", 1, "side", False), ("launch", 2, "cur", True),
+    # graphs are prepared first (tower 1 on the side stream), the streams join (the shared patch embedding would run here),
+    # then both replays, then the outputs are cloned on the caller's stream after the final join
+    assert log == [("wait", "side", "cur"), ("prepare", 1, "side", False), ("prepare", 2, "cur", True),
+                   ("wait", "cur", "side"), ("wait", "side", "cur"), ("replay", 1, "side"), ("replay", 2, "cur"),
                    ("wait", "cur", "side"), ("finish", 1, "cur"), ("finish", 2, "cur")]
     tw.vision_tower_stage2.train()
     with pytest.raises(NotImplementedError):

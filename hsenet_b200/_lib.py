@@ -24,7 +24,7 @@ vp = C.c_void_p
 class BlockWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("w_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
                                   "ln1_g", "ln1_b", "ln2_g", "ln2_b",
-                                  "w_qkv_ln", "cs_qkv", "b_qkv_ln", "w_fc1_ln", "cs_fc1", "b_fc1_ln")]
+                                  "w_qkv_ln", "cs_qkv", "b_qkv_ln", "w_fc1_ln", "cs_fc1", "b_fc1_ln", "b_qkv")]
 
 
 class VitWeights(C.Structure):
@@ -32,6 +32,11 @@ class VitWeights(C.Structure):
         (n, vp) for n in ("cls_token", "pos_embed", "w_patch", "b_patch", "blocks_host", "norm_g", "norm_b",
                           "w_sq", "b_sq", "w_skv", "b_skv", "w_so", "b_so", "sn_g", "sn_b", "w_score", "b_score",
                           "w_patch_f32")]
+
+
+class TrunkWeights(C.Structure):
+    _fields_ = [("num_layers", C.c_int32), ("ln_eps", C.c_float)] + [
+        (n, vp) for n in ("w_patch_sum", "b_patch", "pos_patch", "cls_pos0", "blocks_host", "norm_g", "norm_b")]
 
 
 class PackerWeights(C.Structure):
@@ -102,6 +107,8 @@ SIGNATURES = {
     "hsenet_foreground_bbox": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "hsenet_crop_normalize_resize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "hsenet_fold_layernorm": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "hsenet_slice_trunk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "hsenet_slice_trunk_forward": (C.c_int, [C.POINTER(TrunkWeights), vp, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
     # training path
     "hsenet_transpose_weight": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "hsenet_vit_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

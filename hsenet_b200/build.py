@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("HSENET_BUILD_TAG", "")
 BUILD = os.path.join(CSRC, "_build" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libhsenet_sm100a" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention_tcgen05.cu", "attention_bwd_tcgen05.cu", "patch_embed_tcgen05.cu", "backward.cu", "train.cu", "rowops.cu", "ingest.cu", "verify_fp32.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "attention_tcgen05.cu", "attention_bwd_tcgen05.cu", "patch_embed_tcgen05.cu", "backward.cu", "train.cu", "slice_trunk.cu", "rowops.cu", "ingest.cu", "verify_fp32.cu"]
 HEADERS = ["common.cuh", "kernels.h", "gemm_epilogue.cuh", "composite.cuh", os.path.join("..", "..", "include", "hsenet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -234,6 +234,7 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
         ep.ln_inv_dim = 1.0f / kHidden; ep.ln_eps = kLnEps;
         HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv_ln, kHidden, M, 3 * kHidden, kHidden, ep, st));
       } else {
+        ep.bias = bw.b_qkv;                 // NULL for the MONAI blocks (qkv_bias=False)
         HS_TRY(layernorm_rows<T>(ws.X, kHidden, bw.ln1_g, bw.ln1_b, M, ws.XN, kHidden, nullptr, kSeq, st));
         HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
       }

@@ -114,7 +114,7 @@ int attention_bwd_f32(const float* qkv, const float* out, const float* d_out, co
 // ---- row kernels ------------------------------------------------------------------------------------------------
 template <typename OutT>
 int layernorm_rows(const float* x, long ldx, const float* gamma, const float* beta, long rows, OutT* out, long ldo,
-                   OutT* out2_patch_only, int seq, cudaStream_t stream);
+                   OutT* out2_patch_only, int seq, cudaStream_t stream, float eps = 1e-5f);
 template <typename OutT>
 int im2col_patches(const float* vol, int B, OutT* out, cudaStream_t stream);
 template <typename OutT>
@@ -183,6 +183,10 @@ int score_scale_bwd(const float* dX, const float* XP, const float* Z, const floa
                     const float* scores, float* dXP, float* dZ, float* dg_partial, float* db_partial,
                     float* dws_partial, float* dbs_partial, int B, cudaStream_t st);
 int add_rows(float* out, const float* a, long n, cudaStream_t st);
+
+// slice branch (row f-2): resized slices of the volume as the [B*32*196, 256] patch matrix of a ViT-B/16 stem
+template <typename OutT>
+int slice_patches(const float* vol, OutT* out, int B, cudaStream_t stream);
 
 // integer maps (device-computed, for bit-exact tests against the oracle's closed forms)
 int patch_gather_map(int32_t* out, cudaStream_t stream);      // [2048,1024]

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, long rows,
                                                         OutT* __restrict__ out, long ldo,
-                                                        OutT* __restrict__ out2, int seq) {
+                                                        OutT* __restrict__ out2, int seq, float eps) {
   pdl_prologue_done();
   const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kHidden) + kLnEps);
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kHidden) + eps);
   OutT* o2 = nullptr;
   if (out2 != nullptr) {
     const long b = row / seq;
@@ -497,6 +497,39 @@ __global__ void __launch_bounds__(256) slice_extract_224_kernel(const float* __r
   }
 }
 
+// Slice branch (row f-2): bilinear (32,256,256) -> (32,224,224) resize of the volume (the depth weight is exactly (1,0),
+// vit.py:805) written directly as the 16x16 patch matrix of a ViT-B/16 stem: out[(slice*196 + py*14 + px), iy*16 + ix].
+// The reference expands the slice to 3 identical channels before the stem conv; the channel sum is folded into the
+// weight instead, so one channel is enough.  One thread per 4 consecutive x.
+template <typename OutT>
+__global__ void __launch_bounds__(256) slice_patches_kernel(const float* __restrict__ vol, OutT* __restrict__ out) {
+  const int slice = blockIdx.y;
+  const int y = blockIdx.x * 4 + (threadIdx.x >> 6);       // 56 blocks x 4 rows
+  const int x0 = (threadIdx.x & 63) * 4;
+  if (x0 >= 224) return;
+  const float* src = vol + static_cast<long>(slice) * (256 * 256);
+  const float sc = 256.0f / 224.0f;
+  float fy = sc * (y + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  const int y0 = static_cast<int>(fy);
+  const int y1 = y0 + (y0 < 255 ? 1 : 0);
+  const float ly = fy - y0, hy = 1.f - ly;
+  float r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float fx = sc * (x0 + k + 0.5f) - 0.5f;
+    fx = fx < 0.f ? 0.f : fx;
+    const int xa = static_cast<int>(fx);
+    const int xb = xa + (xa < 255 ? 1 : 0);
+    const float lx = fx - xa, hx = 1.f - lx;
+    r[k] = hy * (hx * __ldg(src + y0 * 256 + xa) + lx * __ldg(src + y0 * 256 + xb)) +
+           ly * (hx * __ldg(src + y1 * 256 + xa) + lx * __ldg(src + y1 * 256 + xb));
+  }
+  const int py = y >> 4, iy = y & 15, px = x0 >> 4, ix = x0 & 15;
+  OutT* o = out + (static_cast<long>(slice) * 196 + py * 14 + px) * 256 + iy * 16 + ix;
+  Vec4<OutT>::store(o, make_float4(r[0], r[1], r[2], r[3]));
+}
+
 __global__ void patch_map_kernel(int32_t* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kNPatch * kPatchDim) out[i] = patch_voxel(i / kPatchDim, i % kPatchDim);
@@ -516,19 +549,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // ---------------------------------------------------------------------------------------------------------------
 template <typename OutT>
 int layernorm_rows(const float* x, long ldx, const float* gamma, const float* beta, long rows, OutT* out, long ldo,
-                   OutT* out2, int seq, cudaStream_t stream) {
+                   OutT* out2, int seq, cudaStream_t stream, float eps) {
   if (rows <= 0) return HS_OK;
   if (!aligned16(x) || (ldx % 4) || (ldo % 4)) return HS_ERR_ALIGN;
   ProfScope prof(PROF_LAYERNORM, 0.0, double(rows) * kHidden * (4.0 + sizeof(OutT) * ((out != nullptr) + (out2 != nullptr))), stream);
   launch_pdl(layernorm_kernel<OutT>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, x, ldx, gamma,
-             beta, rows, out, ldo, out2, seq);
+             beta, rows, out, ldo, out2, seq, eps);
   count_launch();
   return launch_status();
 }
 template int layernorm_rows<float>(const float*, long, const float*, const float*, long, float*, long, float*, int,
-                                   cudaStream_t);
+                                   cudaStream_t, float);
 template int layernorm_rows<__nv_bfloat16>(const float*, long, const float*, const float*, long, __nv_bfloat16*, long,
-                                           __nv_bfloat16*, int, cudaStream_t);
+                                           __nv_bfloat16*, int, cudaStream_t, float);
 
 template <typename OutT>
 int im2col_patches(const float* vol, int B, OutT* out, cudaStream_t stream) {
@@ -715,6 +748,17 @@ int slice_extract(const float* vol, OutT* out, int B, int oh, int ow, cudaStream
 }
 template int slice_extract<float>(const float*, float*, int, int, int, cudaStream_t);
 template int slice_extract<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, cudaStream_t);
+
+template <typename OutT>
+int slice_patches(const float* vol, OutT* out, int B, cudaStream_t stream) {
+  if (B <= 0) return HS_OK;
+  if (!aligned16(vol) || (reinterpret_cast<uintptr_t>(out) & 7)) return HS_ERR_ALIGN;
+  slice_patches_kernel<OutT><<<dim3(56, B * 32), 256, 0, stream>>>(vol, out);
+  count_launch();
+  return launch_status();
+}
+template int slice_patches<float>(const float*, float*, int, cudaStream_t);
+template int slice_patches<__nv_bfloat16>(const float*, __nv_bfloat16*, int, cudaStream_t);
 
 int patch_gather_map(int32_t* out, cudaStream_t stream) {
   patch_map_kernel<<<kNPatch * kPatchDim / 256, 256, 0, stream>>>(out);

@@ -73,6 +73,9 @@ typedef struct hsenet_block_weights {
   const void* w_fc1_ln;   /* bf16 [3072,768]  gamma2 (.) mlp.linear1.weight   */
   const float* cs_fc1;    /* [3072]                                            */
   const float* b_fc1_ln;  /* [3072]           mlp.linear1.bias + weight . beta2 */
+  /* qkv bias [2304]: NULL for the MONAI blocks of the 3D towers (vit.py passes qkv_bias=False); set for the timm blocks of
+   * the slice trunk (hsenet_slice_trunk_forward). */
+  const float* b_qkv;
 } hsenet_block_weights;
 
 /* ViT_stage1 (vit.py:360-469) when stage == 1, ViT_stage2 (vit.py:222-357) when stage == 2. */
@@ -312,6 +315,31 @@ int hsenet_packer_backward(const hsenet_packer_weights* w, const hsenet_packer_w
                            int precision, const void* d_out, const void* tape, size_t tape_bytes,
                            const hsenet_packer_grads* grads, float* d_hr, void* workspace, size_t workspace_bytes,
                            hsenet_stream_t stream);
+
+/* ---- online 2D-slice branch -------------------------------------------------------------
+ * Replaces the offline JPG -> BiomedCLIP -> npy pipeline (Data/data_processing/CT-RATE/CT-RATE_2D_to_npy_file.py:75-98) and
+ * the online formulation of ViT4LLM_v3_med2e3.forward (vit.py:805-808): the 32 slices of a volume are resized to 224x224
+ * (trilinear with unit depth weight == per-slice bilinear), expanded to three identical channels, and encoded by a
+ * ViT-B/16 trunk (timm vit_base_patch16_224 as instantiated by open_clip for BiomedCLIP: 196 patches + cls, 12 pre-LN
+ * blocks with qkv bias, LayerNorm eps 1e-6, exact GELU, token pooling, no head) -> [B,32,768] slice features, the
+ * `images_2d` input of ViT_stage2.  Runs on the same tcgen05 GEMM / attention kernels as the 3D towers (S = 197).
+ * The three identical input channels are folded into the stem: w_patch_sum[o, iy*16+ix] = sum_c conv.weight[o,c,iy,ix]. */
+typedef struct hsenet_trunk_weights {
+  int32_t num_layers;
+  float ln_eps;                            /* 1e-6 for timm ViTs */
+  const void* w_patch_sum;                 /* activation dtype [768,256] */
+  const float* b_patch;                    /* [768] patch_embed.proj.bias */
+  const float* pos_patch;                  /* [196,768] pos_embed[0, 1:] */
+  const float* cls_pos0;                   /* [768] cls_token + pos_embed[0, 0] */
+  const hsenet_block_weights* blocks_host; /* HOST array; b_qkv set; LayerNorm-fold fields unused */
+  const float* norm_g;                     /* final norm */
+  const float* norm_b;
+} hsenet_trunk_weights;
+
+size_t hsenet_slice_trunk_workspace_bytes(int B, int precision);
+/* images fp32 [B,1,32,256,256] -> out fp32 [B*32,768] (pooled cls token after the final norm). */
+int hsenet_slice_trunk_forward(const hsenet_trunk_weights* w, const float* images, int B, int precision, float* out,
+                               void* workspace, size_t workspace_bytes, hsenet_stream_t stream);
 
 /* Operator-level: backward of hsenet_self_attention.  lse / dvec: fp32 [B,12,ceil(S/128)*128]; lse comes from
  * hsenet_self_attention_train. */

@@ -338,3 +338,47 @@ def parity_metrics(got: torch.Tensor, ref: torch.Tensor) -> dict:
     max_rel = float((g - r).abs().max() / (r.abs().max() + 1e-300))
     rms_rel = float((g - r).norm() / (r.norm() + 1e-300))
     return {"cos": cos, "max_rel": max_rel, "rms_rel": rms_rel}
+
+
+# --------------------------------------------------------------------------------------------------
+# Online 2D-slice branch: ViT4LLM_v3_med2e3.forward, vit.py:805-808, and the offline extractor
+# Data/data_processing/CT-RATE/CT-RATE_2D_to_npy_file.py:75-98 (`model.visual.trunk` of BiomedCLIP).
+# PARITY UNPINNED: the trunk is timm 1.0.11's VisionTransformer (vit_base_patch16_224, num_classes=0) created by
+# open_clip 2.24.0 (requirements.txt:73,142); neither package nor the BiomedCLIP weights are available offline.  Restated
+# here from timm's published forward: conv stem (16x16/16) -> cls token prepended -> + pos_embed -> 12 pre-LN blocks
+# (LayerNorm eps 1e-6, qkv WITH bias in (qkv, head, d) order, scale 64^-0.5, exact GELU) -> LayerNorm -> token pooling.
+# --------------------------------------------------------------------------------------------------
+TRUNK_LN_EPS = 1e-6
+
+
+def _ln6(x, sd, prefix):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], TRUNK_LN_EPS)
+
+
+def timm_vit_trunk(sd, x2d: torch.Tensor) -> torch.Tensor:
+    """timm VisionTransformer.forward (forward_features + token pooling, head = Identity): [N,3,224,224] -> [N,768]."""
+    n = x2d.shape[0]
+    x = F.conv2d(x2d, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=16)    # [N,768,14,14]
+    x = x.flatten(2).transpose(1, 2)                                                            # [N,196,768]
+    x = torch.cat((sd["cls_token"].expand(n, -1, -1), x), dim=1) + sd["pos_embed"]
+    i = 0
+    while f"blocks.{i}.norm1.weight" in sd:
+        p = f"blocks.{i}"
+        h = _ln6(x, sd, p + ".norm1")
+        qkv = F.linear(h, sd[p + ".attn.qkv.weight"], sd[p + ".attn.qkv.bias"])
+        qkv = qkv.reshape(n, -1, 3, HEADS, HEAD_DIM).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        att = ((q * HEAD_DIM ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(n, -1, HIDDEN)
+        x = x + F.linear(o, sd[p + ".attn.proj.weight"], sd[p + ".attn.proj.bias"])
+        h = _ln6(x, sd, p + ".norm2")
+        h = F.gelu(F.linear(h, sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"]))
+        x = x + F.linear(h, sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"])
+        i += 1
+    return _ln6(x, sd, "norm")[:, 0]
+
+
+def slice_branch(sd, images: torch.Tensor) -> torch.Tensor:
+    """vit.py:805-808 + :816: resize to (32,224,224), expand to 3 channels, trunk, view(batch, slice_num, -1)."""
+    b = images.shape[0]
+    return timm_vit_trunk(sd, slice_extract(images)).reshape(b, IMG[0], -1)

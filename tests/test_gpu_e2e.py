@@ -303,3 +303,39 @@ def test_input_dtypes_layouts_and_output_dtype(cuda):
         m.blocks[0].mlp.linear2.weight.mul_(2.0)
         y3, _ = m(x, s)
         assert torch.equal(y3, base)
+
+
+@pytest.mark.parametrize("layers", [2, 12])
+def test_slice_trunk_online_branch(cuda, layers):
+    """Row f-2: volume -> 32 resized slices -> ViT-B/16 trunk -> [B,32,768], against the restated timm forward (parity
+    unpinned at the timm / open_clip boundary: neither is installable offline).  The result feeds ViT_stage2 as image_2d."""
+    import hsenet_b200 as H
+    torch.manual_seed(3)
+    m = H.SliceTrunkViTB16(num_layers=layers).eval()
+    g = torch.Generator().manual_seed(17)
+    with torch.no_grad():
+        for name, p in m.named_parameters():          # timm-like scales; norms / biases perturbed so they cannot hide
+            if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name == "norm.weight":
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif name.endswith("bias"):
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+            elif name == "cls_token":
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    assert len(m.state_dict()) == 4 + 12 * layers + 2
+    sd = cpu_state(m)
+    x, _ = synthetic_inputs(1, seed=9)
+    ref = O.slice_branch(sd, x)
+    m = m.to(cuda)
+    with torch.no_grad():
+        with H.precision("fp32_verify"):
+            got = m(x.to(cuda))
+        assert got.shape == (1, 32, 768) and got.dtype == torch.float32
+        print("slice trunk fp32_verify", assert_fp32(got, ref, "slice trunk fp32"))
+        with H.precision("bf16"):
+            got = m(x.to(cuda))
+        print("slice trunk bf16", assert_bf16(got, ref, "slice trunk bf16"))
+        # feeds the 2E3 encoder in place of the offline npy features
+        t2 = _build(H.ViT_stage2, 1).to(cuda).requires_grad_(False)
+        with H.precision("bf16"):
+            y, _ = t2(x.to(cuda), got)
+        assert y.shape == (1, 2049, 768) and torch.isfinite(y.float()).all()

@@ -527,7 +527,8 @@ def main():
             "launches": int(ln[0]), "avg_launch_ms": ms[0] / ln[0] if ln[0] else None,
             "how": "algorithmic 2*M*N*K per launch / CUDA-event duration per launch, instrumented re-run of the same steps",
         },
-        "roofline_attention": {"kernel": "attention_split_kernel (tcgen05 flash attention; 31% of FLOPs)",
+        "roofline_attention": {"kernel": {"s": "attention_split_kernel", "t": "attention_kernel<POLY,3>", "r": "attention_kernel<POLY,2>"}[
+                                   (os.environ.get("HSENET_ATT_KERNEL") or "split")[0]] + " (tcgen05 flash attention; 31% of FLOPs)",
                                "bound": "mufu" if att_bounds["mufu"]["frac"] > att_bounds["tensor"]["frac"] else "tensor",
                                "achieved": att_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                                "frac": att_tf / peaks["bf16_sustained"], "bounds": att_bounds, "launches": int(ln[1]),

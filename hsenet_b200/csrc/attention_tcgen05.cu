@@ -773,11 +773,11 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int
                  stream);
   const char* e = std::getenv("HSENET_ATT_POLY");        // share of exponentials emulated on the FMA pipe (0 / 2 / 4 of 8)
   const int poly = e != nullptr ? std::atoi(e) : kDefaultPoly;
-  // HSENET_ATT_KERNEL (A/B runs): "tri" (default) = 4 softmax warps, three aliased S/P buffers; "rowwarp" = the round-1
-  // kernel (two S + two P buffers); "split" = 8 softmax warps splitting every step by key half (two O accumulators)
+  // HSENET_ATT_KERNEL (A/B runs): "split" (default) = 8 softmax warps splitting every step by key half (two O accumulators);
+  // "tri" = 4 softmax warps, three aliased S/P buffers; "rowwarp" = the round-1 layout (two S + two P buffers)
   const char* kv = std::getenv("HSENET_ATT_KERNEL");
-  const bool split = kv != nullptr && kv[0] == 's';
-  const bool tri = !(kv != nullptr && kv[0] == 'r');
+  const bool split = kv == nullptr || kv[0] == 's';
+  const bool tri = kv != nullptr && kv[0] == 't';
   const dim3 grid((S + QT - 1) / QT, kHeads, B);
   if (split) {
     if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);

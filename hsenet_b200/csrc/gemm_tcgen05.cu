@@ -24,6 +24,13 @@ extern void count_launch();
 
 namespace {
 
+#ifndef HSENET_GEMM_PARK
+#define HSENET_GEMM_PARK 1
+#endif
+__device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity) {
+  if (HSENET_GEMM_PARK) mbar_wait_parked(bar, parity); else mbar_wait_nocall(bar, parity);
+}
+
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
@@ -95,7 +102,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait_nocall(&bars->empty[s], phase ^ 1);
+        gwait(&bars->empty[s], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
           tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmA, &bars->full[s], kb * BK, m0);
@@ -113,11 +120,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait_nocall(&bars->tmem_empty[acc], acc_phase ^ 1);
+      gwait(&bars->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait_nocall(&bars->full[s], phase);
+        gwait(&bars->full[s], phase);
         tc_fence_after();
         const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
@@ -155,7 +162,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
       if (tile + tile_step < total_tiles)
         epilogue_ln_load<MODE>(ep, next_m0(tile + tile_step) + quarter * 32, M, lane, ln_sq);
-      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      gwait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       uint64_t* empty_bar = &bars->tmem_empty[acc];
       epilogue_slab<MODE>(ep, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_half * 128, stage,

@@ -28,6 +28,14 @@ int gemm_bf16_1cta(const void* A, int lda, const void* W, int ldw, int M, int N,
 
 namespace {
 
+#ifndef HSENET_GEMM_PARK
+#define HSENET_GEMM_PARK 1
+#endif
+// all waits of the kernel: parked try_wait (suspend-time hint) by default; HSENET_GEMM_PARK=0 builds spin for A/B runs
+__device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity) {
+  if (HSENET_GEMM_PARK) mbar_wait_parked(bar, parity); else mbar_wait_nocall(bar, parity);
+}
+
 constexpr int PM = 256;                     // pair tile rows   (128 per CTA)
 constexpr int PN = 256;                     // pair tile cols   (each CTA stages 128 of the 256 W rows)
 constexpr int BK = 128;                     // K per pipeline stage = two 64-column (128-byte swizzle) TMA boxes per operand
@@ -156,7 +164,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int m0 = (tile / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
       const int n0 = (tile % n_tiles) * PN + static_cast<int>(cta_rank) * 128;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait_nocall(&bars->empty[s], phase ^ 1);
+        gwait(&bars->empty[s], phase ^ 1);
         if (elect_one()) {
           if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
           tma_load_2d_2cta(smem_a + s * A_STAGE_BYTES, &tmA, &bars->full[s], kb * BK, m0, kEvictNormal);
@@ -179,11 +187,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-        mbar_wait_nocall(&bars->tmem_empty[acc], acc_phase ^ 1);
+        gwait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_nocall(&bars->full[s], phase);
+          gwait(&bars->full[s], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
@@ -223,7 +231,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
       if (tile + tile_step < total_tiles)
         epilogue_ln_load<MODE>(ep, next_m0(tile + tile_step) + quarter * 32, M, lane, ln_sq);
-      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      gwait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       uint64_t* empty_bar = &bars->tmem_empty[acc];
       epilogue_slab<MODE>(ep, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * PN + col_half * 128, stage,

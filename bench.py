@@ -247,6 +247,30 @@ def measure_clip_step(enc, dev, rank, world, x, s, barrier, max_over_ranks, step
                      "(bit-exact), own block == local embeddings, logits finite; MIN-reduced over ranks"}
 
 
+def measure_train_step(dev, B=8, steps=3):
+    """forward + backward of a trainable 12-layer ViT_stage1 through the autograd Function
+    (stage-1 CLIP image side, train_CLIP_stage1.py:231-257), batch 8, bf16.  An extra record, not the headline."""
+    import hsenet_b200 as H
+    torch.manual_seed(0)
+    vit = H.ViT_stage1(1, (32, 256, 256), (4, 16, 16), pos_embed="perceptron", spatial_dims=3, classification=True).to(dev)
+    x = torch.rand(B, 1, 32, 256, 256, generator=torch.Generator().manual_seed(5)).to(dev)
+
+    def step():
+        vit.zero_grad(set_to_none=True)
+        y, _ = vit(x)
+        y.float().square().mean().backward()
+
+    step()
+    ms = _event_ms(step, steps, dev)
+    finite = all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in vit.parameters())
+    del vit
+    H.release_workspaces()
+    torch.cuda.empty_cache()
+    return {"workload": "ViT_stage1 (12 layers) forward + backward through hsenet_vit_forward_train / hsenet_vit_backward",
+            "value": B / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms, "volumes_per_step": B, "steps": steps,
+            "tflops_at_3x_forward": 3 * 506.05 * B / ms, "grads_finite": finite}
+
+
 def gpu_eager_baseline(enc, dev, B=8, reps=3):
     """The reference algorithm (oracle port of vit.py / packer, materialised scores, eager PyTorch kernels) on the SAME
     B200 under bf16 autocast: BASELINE.md section 4's 'reference on the same box' number.  A baseline leg, like cpu_baseline."""
@@ -472,6 +496,11 @@ def main():
                     extras["gpu_eager_baseline"] = gpu_eager_baseline(enc, dev)
                 except Exception as exc:                       # a baseline leg must never take the bench line down
                     extras["gpu_eager_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+                try:
+                    with torch.enable_grad():
+                        extras["train_step"] = measure_train_step(dev)
+                except Exception as exc:
+                    extras["train_step"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
     if rank != 0:
         if world > 1:

@@ -46,6 +46,17 @@ constexpr int ATT_THREADS = 224;   // producer warp, two MMA-issuing warps, four
 #define HSENET_ATT_EARLY_PROBE 0   // measured slower in both forms (register result: +4..9 %, deferred named predicate: +3..7 %)
 #endif
 constexpr bool kEarlyProbe = HSENET_ATT_EARLY_PROBE != 0;
+#ifndef HSENET_ATT_TRACE_WARP
+#define HSENET_ATT_TRACE_WARP 3
+#endif
+#ifndef HSENET_ATT_SINGLE_ISSUER
+#define HSENET_ATT_SINGLE_ISSUER 1
+#endif
+constexpr bool kSingleIssuer = HSENET_ATT_SINGLE_ISSUER != 0;
+#ifndef HSENET_ATT_PV_INTERLEAVE
+#define HSENET_ATT_PV_INTERLEAVE 1
+#endif
+constexpr bool kPvInterleave = HSENET_ATT_PV_INTERLEAVE != 0;
 #ifndef HSENET_ATT_PARK
 #define HSENET_ATT_PARK 1
 #endif
@@ -100,10 +111,14 @@ __device__ unsigned long long g_att_trace[48];   // [0,16) softmax warp 2, [16,3
     g_att_trace[(base) + 14] = clock64() - tstart;                                     \
     g_att_trace[(base) + 15] = nsub;                                                   \
   }
+__device__ long long g_att_times[12][48];         // rows 0..7: p_full arrive of softmax warp r; 8: s_full seen (warp 3); 9: issuer woken; 10: issue end
+#define ATT_TS(row, step)                                                                          \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (step) < 48) g_att_times[row][step] = clock64()
 #else
 #define ATT_TR(i)
 #define ATT_TR_DECL
 #define ATT_TR_DUMP(base)
+#define ATT_TS(row, step)
 #endif
 
 __device__ __forceinline__ float ex2(float x) {
@@ -405,7 +420,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     const bool ragged = (S % KS) != 0;
     for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
     if (ragged) softmax_step(nsub - 1, std::true_type{});
-    if (warp == 3 && lane == 0) { ATT_TR_DUMP(0); }
+    if (warp == HSENET_ATT_TRACE_WARP && lane == 0) { ATT_TR_DUMP(0); }
     // ---- epilogue: O / l -> bf16 -> out[b*S + qi, h*64 .. h*64+63] -----------------------------------------------
     if (nsub >= 2) smx_wait(&bars->pv_done[(nsub - 2) & 1], ((nsub - 2) >> 1) & 1);
     smx_wait(&bars->pv_done[(nsub - 1) & 1], ((nsub - 1) >> 1) & 1);
@@ -513,17 +528,58 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     constexpr uint32_t idesc_pv = make_idesc_bf16(QT, kHeadDim, 0, 1);
     const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ));
     auto issue_qk = [&](const int t) {
-      const int ks = (t >> 1) % K_STAGES;
-      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + par * SUB_BYTES));
+      const int ks = (t >> 1) % K_STAGES, sub = t & 1;
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE_BYTES + sub * SUB_BYTES));
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ss(tmem_base + ATS_COL_S + par * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        tc_commit(&bars->s_full[par]);
+          umma_ss(tmem_base + ATS_COL_S + sub * KS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        tc_commit(&bars->s_full[sub]);
         tc_commit(&bars->k_empty[ks]);
       }
       __syncwarp();
     };
+    if (kSingleIssuer) {
+      // ONE issuing warp for every step: P V (t) then Q K^T (t+2), all MMAs of the CTA in program order.  With two issuing
+      // warps (round 1: needed because a diverged single-lane issuer cost ~1200 cycles per step) P V (t) had to wait for
+      // the COMPLETION of the other warp's P V (t-1) to keep the accumulation order fixed, which put a full MMA round trip
+      // (tools/attn_timeline.py: 500-950 cycles from the softmax warps' arrive to the issuer's wake-up) on the cycle.
+      if (par != 0) return;
+      ctl_wait(&bars->q_full, 0);
+      ctl_wait(&bars->k_full[0], 0);
+      issue_qk(0);
+      if (nsub > 1) issue_qk(1);
+      ATT_TR_DECL;
+      for (int t = 0; t < nsub; ++t) {
+        const int sub = t & 1, j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
+        ctl_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+        if (t2 < nsub) ctl_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
+        ATT_TR(0);
+        ctl_wait(&bars->p_full[sub], (t >> 1) & 1);
+        if (lane == 0) { ATT_TS(9, t); }
+        tc_fence_after();
+        ATT_TR(1);
+        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + sub * SUB_BYTES));
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < KS / 16; ++i) {
+            const int k = kPvInterleave ? ((i & 1) * 2 + (i >> 1)) : i;
+            const int half = k >> 1;
+            umma_ts(tmem_base + ATS_COL_O + half * kHeadDim, tmem_base + ATS_COL_S + sub * KS + half * 32 + 8 * (k & 1),
+                    vdesc + 128 * k, idesc_pv, (t | (k & 1)) != 0 ? 1u : 0u);
+          }
+          tc_commit(&bars->pv_done[sub]);
+          tc_commit(&bars->v_empty[vs]);
+        }
+        __syncwarp();
+        ATT_TR(2);
+        if (t2 < nsub) issue_qk(t2);
+        if (lane == 0) { ATT_TS(10, t); }
+        ATT_TR(3);
+      }
+      ATT_TR_DUMP(16);
+      return;
+    }
     if (par >= nsub) return;
     ctl_wait(&bars->q_full, 0);
     ctl_wait(&bars->k_full[0], 0);
@@ -536,13 +592,17 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       if (t >= 1) ctl_wait(&bars->pv_done[par ^ 1], ((t - 1) >> 1) & 1);   // keep the accumulation order fixed
       ATT_TR(0);
       ctl_wait(&bars->p_full[par], (t >> 1) & 1);
+      if (lane == 0) { ATT_TS(9, t); }
       tc_fence_after();
       ATT_TR(1);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE_BYTES + par * SUB_BYTES));
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KS / 16; ++k) {
-          // key half k>>1: A = 16 keys = 8 packed columns at the start of that half's score columns, D = that half's O
+        for (int i = 0; i < KS / 16; ++i) {
+          // key half k>>1: A = 16 keys = 8 packed columns at the start of that half's score columns, D = that half's O.
+          // Issue order k = 0, 2, 1, 3: consecutive MMAs alternate between the two accumulators (back-to-back MMAs into
+          // the SAME accumulator occupy the pipe ~57 cycles instead of ~48, tools/umma_throughput.cu)
+          const int k = kPvInterleave ? ((i & 1) * 2 + (i >> 1)) : i;
           const int half = k >> 1;
           umma_ts(tmem_base + ATS_COL_O + half * kHeadDim, tmem_base + ATS_COL_S + par * KS + half * 32 + 8 * (k & 1),
                   vdesc + 128 * k, idesc_pv, (t | (k & 1)) != 0 ? 1u : 0u);
@@ -553,6 +613,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       __syncwarp();
       ATT_TR(2);
       if (t2 < nsub) issue_qk(t2);
+      if (lane == 0) { ATT_TS(10, t); }
       ATT_TR(3);
     }
     ATT_TR_DUMP(16 + 16 * par);
@@ -590,7 +651,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
   } else if (warp == 1) {
     mma_issuer(0);
   } else if (warp == 2) {
-    mma_issuer(1);
+    mma_issuer(1);        // returns at once in the single-issuer configuration
   } else {
     // ===================== softmax warps: quarter = TMEM lane quarter (warp % 4), half = key half =====================
     const int quarter = warp & 3;
@@ -612,8 +673,10 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       } else {
         smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
       }
-      tc_fence_after();
       ATT_TR(0);
+      if (warp == 3 && lane == 0) { ATT_TS(8, t); }
+      tc_fence_after();
+      ATT_TR(2);
       uint32_t x[32];
       uint32_t pk[16];
       float alpha = 1.f;
@@ -694,12 +757,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
+      if (lane == 0) { ATT_TS(warp - 3, t); }
       ATT_TR(7);
     };
     const bool ragged = (S % KS) != 0;
     for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
     if (ragged) softmax_step(nsub - 1, std::true_type{});
-    if (warp == 3 && lane == 0) { ATT_TR_DUMP(0); }
+    if (warp == HSENET_ATT_TRACE_WARP && lane == 0) { ATT_TR_DUMP(0); }
     // ---- merge the two key halves and store: this warp takes output columns [half*32, half*32+32) of its 32 rows ----
     ml[half * 128 + quarter * 32 + lane] = make_float2(m, l);
     asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 softmax warps only
@@ -799,6 +863,9 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int
 }  // namespace hs
 
 #ifdef HSENET_ATT_TRACE
+extern "C" int hsenet_debug_att_times(long long* host576) {
+  return cudaMemcpyFromSymbol(host576, hs::g_att_times, sizeof(long long) * 576) == cudaSuccess ? 0 : -4;
+}
 extern "C" int hsenet_debug_att_trace(unsigned long long* host48) {
   return cudaMemcpyFromSymbol(host48, hs::g_att_trace, sizeof(unsigned long long) * 48) == cudaSuccess ? 0 : -4;
 }

@@ -98,13 +98,43 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const TIn* __restric
   }
 }
 
-// out[n] = sum_t partial[t][n] in index order
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int T, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// out[n] = sum_t partial[t][n], T rows of N columns, fixed summation order (deterministic).
+// Tall case (bias / LayerNorm partials: T ~ 257, N <= 3072): block = 32 columns x 32 row groups, each thread sums its
+// contiguous slice of t (loads unrolled so they overlap), the 32 slice sums are added in index order.  (A first version
+// walked all T rows in one thread: 29 us of dependent DRAM latency per call, 8 % of a training step.)
+__global__ void __launch_bounds__(1024) colsum_finish_tall_kernel(const float* __restrict__ partial, int T, int N,
+                                                                  float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int per = (T + 31) / 32;
+  const int t0 = ty * per, t1 = min(T, t0 + per);
   float s = 0.f;
-  for (int t = 0; t < T; ++t) s += partial[static_cast<long>(t) * N + n];
-  out[n] = s;
+  if (n < N) {
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t) s += __ldg(partial + static_cast<long>(t) * N + n);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float a = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) a += red[g][tx];
+    out[n] = a;
+  }
+}
+// Flat case (split-K partials of a weight gradient: T <= 8 slices of up to 2.4 M elements): one float4 per thread
+__global__ void __launch_bounds__(256) colsum_finish_flat_kernel(const float* __restrict__ partial, int T, long n4,
+                                                                 float* __restrict__ out) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(partial) + i);
+    for (int t = 1; t < T; ++t) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + t * n4 + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -605,7 +635,14 @@ template int transpose_pad<__nv_bfloat16, __nv_bfloat16>(const __nv_bfloat16*, l
 
 int colsum_finish(const float* partial, int T, int N, float* out, cudaStream_t st) {
   if (N <= 0) return HS_OK;
-  colsum_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, T, N, out);
+  if (T <= 8 && N % 4 == 0 && N >= 4096) {
+    const long n4 = N / 4;
+    long blocks = (n4 + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    colsum_finish_flat_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(partial, T, n4, out);
+  } else {
+    colsum_finish_tall_kernel<<<(N + 31) / 32, 1024, 0, st>>>(partial, T, N, out);
+  }
   count_launch();
   return launch_status();
 }

@@ -114,7 +114,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const GemmEpilogue ep, int M, int N, int K) {
+                      const GemmEpilogue ep_in, int M, int N, int K, int ksplit, int kb_per, long split_stride) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -129,7 +129,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int num_pairs = gridDim.x >> 1;
   const int n_tiles = N / PN;
   const int m_tiles = (M + PM - 1) / PM;
-  const int total_tiles = n_tiles * m_tiles;
+  const int mn_tiles = n_tiles * m_tiles;
+  const int total_tiles = mn_tiles * ksplit;      // split-K: tile = (k slice, m tile, n tile); slices write separate partials
   const int k_blocks = K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -161,9 +162,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int s = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-      const int m0 = (tile / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
-      const int n0 = (tile % n_tiles) * PN + static_cast<int>(cta_rank) * 128;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int m0 = (mn / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
+      const int n0 = (mn % n_tiles) * PN + static_cast<int>(cta_rank) * 128;
+      const int kb0 = ks * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         gwait(&bars->empty[s], phase ^ 1);
         if (elect_one()) {
           if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[s], 2 * STAGE_BYTES);
@@ -190,7 +193,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         gwait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = (tile / mn_tiles) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           gwait(&bars->full[s], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
@@ -201,10 +205,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint32_t off = (k >> 2) * (SUB_BYTES >> 4) + 2 * (k & 3);
-              umma_ss_2cta(tmem_d, adesc + off, bdesc + off, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss_2cta(tmem_d, adesc + off, bdesc + off, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             }
             tc_commit_2cta(&bars->empty[s]);
-            if (kb == k_blocks - 1) tc_commit_2cta(&bars->tmem_full[acc]);
+            if (kb == kb1 - 1) tc_commit_2cta(&bars->tmem_full[acc]);
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; phase ^= 1; }
@@ -221,12 +225,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     const int tile_step = num_pairs;
-    auto next_m0 = [&](int t) { return (t / n_tiles) * PM + static_cast<int>(cta_rank) * 128; };
+    auto next_m0 = [&](int t) { return ((t % mn_tiles) / n_tiles) * PM + static_cast<int>(cta_rank) * 128; };
+    const GemmEpilogue& ep = ep_in;
     float2 ln_sq[8];
     if (pair < total_tiles) epilogue_ln_load<MODE>(ep, next_m0(pair) + quarter * 32, M, lane, ln_sq);
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
-      const int m0 = (tile / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
-      const int n0 = (tile % n_tiles) * PN;
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int m0 = (mn / n_tiles) * PM + static_cast<int>(cta_rank) * 128;
+      const int n0 = (mn % n_tiles) * PN;
+      GemmEpilogue ept = ep_in;                 // split-K: slice ks writes its own fp32 partial
+      if (ksplit > 1) ept.out_f32 = ep_in.out_f32 + ks * split_stride;
       float ln_a[8], ln_b[8];
       epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
       if (tile + tile_step < total_tiles)
@@ -234,7 +242,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       gwait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       uint64_t* empty_bar = &bars->tmem_empty[acc];
-      epilogue_slab<MODE>(ep, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * PN + col_half * 128, stage,
+      epilogue_slab<MODE>(ept, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * PN + col_half * 128, stage,
                     m0 + quarter * 32, n0 + col_half * 128, M, N, lane, ln_a, ln_b, [&]() {
                       tc_fence_before();
                       __syncwarp();
@@ -255,7 +263,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }  // namespace
 
 int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int ksplit = 1, long split_stride = 0) {
   if (M <= 0) return HS_OK;
   if (N % PN != 0 || K % BK != 0) return HS_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (lda % 8) || (ldw % 8))
@@ -280,22 +288,41 @@ int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N,
     ok &= cudaFuncSetAttribute(gemm_bf16_2cta_kernel<EPI_F32_RESID_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     if (!ok) return HS_ERR_CUDA;
   }
-  const int tiles = (N / PN) * ((M + PM - 1) / PM);
+  const int k_blocks = K / BK;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > k_blocks) ksplit = k_blocks;
+  const int kb_per = (k_blocks + ksplit - 1) / ksplit;
+  ksplit = (k_blocks + kb_per - 1) / kb_per;            // no empty slice
+  const int tiles = (N / PN) * ((M + PM - 1) / PM) * ksplit;
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const int grid = 2 * pairs;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 2.0 * (double(M) * K + double(N) * K + double(M) * N), stream);
   switch (epilogue_mode(ep)) {
-    case EPI_BF16: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
-    case EPI_BF16_GELU: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
-    case EPI_F32_RESID: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
-    case EPI_BF16_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
-    case EPI_BF16_GELU_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
-    case EPI_F32_RESID_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
-    default: launch_pdl(gemm_bf16_2cta_kernel<EPI_GENERIC>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K); break;
+    case EPI_BF16: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
+    case EPI_BF16_GELU: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
+    case EPI_F32_RESID: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
+    case EPI_BF16_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
+    case EPI_BF16_GELU_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
+    case EPI_F32_RESID_LN: launch_pdl(gemm_bf16_2cta_kernel<EPI_F32_RESID_LN>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
+    default: launch_pdl(gemm_bf16_2cta_kernel<EPI_GENERIC>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
   }
   count_launch();
   return cudaGetLastError() == cudaSuccess ? HS_OK : HS_ERR_CUDA;
+}
+
+// Split-K GEMM for the weight gradients (M, N small, K = the token dimension): `ksplit` K slices run as independent tiles and
+// write fp32 partials [ksplit][M][N] (finish with a fixed-order sum).  Returns the number of slices actually used.
+int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* partials, int ksplit,
+                     cudaStream_t stream, int* used) {
+  const int k_blocks = K / BK;
+  if (ksplit > k_blocks) ksplit = k_blocks;
+  if (ksplit < 1) ksplit = 1;
+  const int kb_per = (k_blocks + ksplit - 1) / ksplit;
+  *used = (k_blocks + kb_per - 1) / kb_per;
+  GemmEpilogue ep;
+  ep.out_f32 = partials; ep.ld_f32 = N;
+  return gemm_bf16_2cta(A, lda, W, ldw, M, N, K, ep, stream, ksplit, static_cast<long>(M) * N);
 }
 
 // Dispatcher: CTA pairs for everything with more than one 128-row tile; HSENET_GEMM_1CTA=1 forces the 1-CTA kernel.

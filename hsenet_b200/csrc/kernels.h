@@ -89,6 +89,9 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64
 // ---- dense contractions -------------------------------------------------------------------------------------
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
               cudaStream_t stream);
+// Split-K variant for the weight gradients: fp32 partials [slices][M][N]; *used = number of slices written.
+int gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* partials, int ksplit,
+                     cudaStream_t stream, int* used);
 // fp32 verification GEMM (CUDA cores, fp32 operands and accumulation); ep.out_bf16 is reinterpreted as float*.
 int gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
              cudaStream_t stream);

@@ -11,8 +11,12 @@
 #include "composite.cuh"
 #include "kernels.h"
 
+#include <type_traits>
+
 namespace hs {
 namespace {
+
+constexpr size_t kDwPartialFloats = 6u << 20;     // split-K partials of one weight gradient (24 MB)
 
 // ---- shared scratch of a training forward / backward ------------------------------------------------------------------
 template <typename T>
@@ -35,6 +39,7 @@ struct TrainWs {
   float* dSm;     // [Mp,32]
   float* dSKV;    // [B*32,1536]
   float* SP;      // [3][nblkp,768] + [nblkp]  score partials
+  float* DWP;     // split-K partials of a weight gradient
   size_t total;
   int Mpad, nblk, nblkp;
   TrainWs(void* base, int B) {
@@ -60,6 +65,7 @@ struct TrainWs {
     dSm = b.take<float>(Mp * kNSlice);
     dSKV = b.take<float>(static_cast<size_t>(B) * kNSlice * 2 * kHidden);
     SP = b.take<float>(3 * static_cast<size_t>(nblkp) * kHidden + nblkp);
+    DWP = b.take<float>(kDwPartialFloats);
     total = b.off;
   }
 };
@@ -112,10 +118,24 @@ struct VitTape {
   }
 };
 
-// dW [N,K] fp32 = dY^T X from the transposed operands dYt [N,Mpad], Xt [K,Mpad]
+// dW [N,K] fp32 = dY^T X from the transposed operands dYt [N,Mpad], Xt [K,Mpad].  The output has few tiles (9 .. 36 of
+// 256x256) and a long contraction (the token dimension): on the tensor-core path the contraction is split into slices that
+// run as independent tiles and write fp32 partials, summed in fixed order (deterministic; one wave of 74 CTA pairs instead
+// of 9 .. 36 busy pairs -- 122 us per weight gradient before).
 template <typename T>
-int grad_weight(const T* dYt, const T* Xt, int N, int K, int Mpad, float* dW, cudaStream_t st) {
+int grad_weight(const T* dYt, const T* Xt, int N, int K, int Mpad, float* dW, float* partials, cudaStream_t st) {
   if (dW == nullptr) return HS_OK;
+  if (std::is_same<T, __nv_bfloat16>::value && partials != nullptr && Mpad % 128 == 0 && N > 128) {
+    const int tiles = ((N + 255) / 256) * (K / 256);
+    int split = tiles > 0 ? (num_sms() / 2) / tiles : 1;
+    if (split > 8) split = 8;
+    while (split > 1 && static_cast<size_t>(split) * N * K > kDwPartialFloats) --split;
+    if (split > 1) {
+      int used = 1;
+      HS_TRY(gemm_bf16_splitk(dYt, Mpad, Xt, Mpad, N, K, Mpad, partials, split, st, &used));
+      return colsum_finish(partials, used, N * K, dW, st);
+    }
+  }
   GemmEpilogue ep;
   ep.out_f32 = dW; ep.ld_f32 = K;
   return Prec<T>::gemm(dYt, Mpad, Xt, Mpad, N, K, Mpad, ep, st);
@@ -239,7 +259,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     if (bg.b_fc2) HS_TRY(colsum_finish(ws.CS, Mpad / 64, kHidden, bg.b_fc2, st));
     // dW2 = dy2^T gelu(h1): the hidden activation is recomputed from the taped pre-activation while it is transposed
     HS_TRY((transpose_pad<T, T>(tp.H1[l], kMlp, M, kMlp, ws.TB, nullptr, 0, 1, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kMlp, Mpad, bg.w_fc2, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kMlp, Mpad, bg.w_fc2, ws.DWP, st));
     {
       GemmEpilogue ep;   // dh1 = (dy2 W2) o gelu'(h1)
       set_act_out(ep, ws.dH, kMlp);
@@ -249,7 +269,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     HS_TRY((transpose_pad<T, T>(ws.dH, kMlp, M, kMlp, ws.TA, nullptr, 0, 0, bg.b_fc1 ? ws.CS : nullptr, st)));
     if (bg.b_fc1) HS_TRY(colsum_finish(ws.CS, Mpad / 64, kMlp, bg.b_fc1, st));
     HS_TRY((transpose_pad<T, T>(tp.XN2[l], kHidden, M, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kMlp, kHidden, Mpad, bg.w_fc1, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kMlp, kHidden, Mpad, bg.w_fc1, ws.DWP, st));
     {
       GemmEpilogue ep;   // d norm2 output = dh1 W1
       ep.out_f32 = ws.dXN; ep.ld_f32 = kHidden;
@@ -264,7 +284,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     HS_TRY((transpose_pad<float, T>(ws.dX, kHidden, M, kHidden, ws.TA, ws.dYb, kHidden, 0, bg.b_out ? ws.CS : nullptr, st)));
     if (bg.b_out) HS_TRY(colsum_finish(ws.CS, Mpad / 64, kHidden, bg.b_out, st));
     HS_TRY((transpose_pad<T, T>(tp.ATT[l], kHidden, M, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mpad, bg.w_out, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mpad, bg.w_out, ws.DWP, st));
     {
       GemmEpilogue ep;   // d attention output = dy W_out
       set_act_out(ep, ws.dATT, kHidden);
@@ -274,7 +294,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     HS_TRY(Prec<T>::attention_bwd(tp.QKV[l], tp.ATT[l], ws.dATT, tp.LSE[l], ws.DVEC, dQKV, B, kSeq, st));
     HS_TRY((transpose_pad<T, T>(dQKV, 3 * kHidden, M, 3 * kHidden, ws.TA, nullptr, 0, 0, nullptr, st)));
     HS_TRY((transpose_pad<T, T>(tp.XN1[l], kHidden, M, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, 3 * kHidden, kHidden, Mpad, bg.w_qkv, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, 3 * kHidden, kHidden, Mpad, bg.w_qkv, ws.DWP, st));
     {
       GemmEpilogue ep;   // d norm1 output = dqkv W_qkv
       ep.out_f32 = ws.dXN; ep.ld_f32 = kHidden;
@@ -308,7 +328,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     HS_TRY((transpose_pad<float, T>(ws.dZ, kHidden, Mp, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_so ? ws.CS : nullptr, st)));
     if (g->b_so) HS_TRY(colsum_finish(ws.CS, Mppad / 64, kHidden, g->b_so, st));
     HS_TRY((transpose_pad<T, T>(tp.O, kHidden, Mp, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mppad, g->w_so, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mppad, g->w_so, ws.DWP, st));
     {
       GemmEpilogue ep;   // dO = dZ W_so
       set_act_out(ep, ws.dATT, kHidden);
@@ -324,13 +344,13 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
                                       g->b_skv ? ws.CS : nullptr, st)));
       if (g->b_skv) HS_TRY(colsum_finish(ws.CS, Rpad / 64, 2 * kHidden, g->b_skv, st));
       HS_TRY((transpose_pad<T, T>(tp.S16, kHidden, R, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-      HS_TRY(grad_weight<T>(ws.TA, ws.TB, 2 * kHidden, kHidden, Rpad, g->w_skv, st));
+      HS_TRY(grad_weight<T>(ws.TA, ws.TB, 2 * kHidden, kHidden, Rpad, g->w_skv, ws.DWP, st));
     }
     // Wq: dW = dQ^T XPa, db = colsum(dQ), dXP += dQ Wq
     HS_TRY((transpose_pad<float, T>(dQ, kHidden, Mp, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_sq ? ws.CS : nullptr, st)));
     if (g->b_sq) HS_TRY(colsum_finish(ws.CS, Mppad / 64, kHidden, g->b_sq, st));
     HS_TRY((transpose_pad<T, T>(tp.XPa, kHidden, Mp, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mppad, g->w_sq, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mppad, g->w_sq, ws.DWP, st));
     {
       GemmEpilogue ep;   // dXP (score path) = dQ Wq, added to the gating path already in dXP
       ep.resid = ws.dXP; ep.ld_resid = kHidden; ep.out_f32 = ws.dXP; ep.ld_f32 = kHidden;
@@ -357,7 +377,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
       T* P = ws.H2;
       HS_TRY(im2col_patches<T>(images, B, P, st));
       HS_TRY((transpose_pad<T, T>(P, kPatchDim, Mp, kPatchDim, ws.TB, nullptr, 0, 0, nullptr, st)));
-      HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kPatchDim, Mppad, g->w_patch, st));
+      HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kPatchDim, Mppad, g->w_patch, ws.DWP, st));
     }
   }
   return HS_OK;
@@ -403,6 +423,7 @@ struct PackerTrainWs {
   T* TB;        // [max(D,768), max(Mwpad, Mppad)]
   float* CS;    // [Mppad/64, max(D,1536)]
   float* LNP;   // [2][nblk,768]
+  float* DWP;   // split-K partials of a weight gradient
   size_t total;
   int Mwpad, Mppad, nblk;
   PackerTrainWs(void* base, int B, int D) {
@@ -423,6 +444,7 @@ struct PackerTrainWs {
     TB = b.take<T>(wide * Mppad);
     CS = b.take<float>(static_cast<size_t>(Mppad / 64) * wide);
     LNP = b.take<float>(2 * static_cast<size_t>(nblk) * kHidden);
+    DWP = b.take<float>(kDwPartialFloats);
     total = b.off;
   }
 };
@@ -484,7 +506,7 @@ int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_
   HS_TRY((transpose_pad<T, T>(d_out, D, Mw, D, ws.TA, nullptr, 0, 0, g->b_p2 ? ws.CS : nullptr, st)));
   if (g->b_p2) HS_TRY(colsum_finish(ws.CS, Mwpad / 64, D, g->b_p2, st));
   HS_TRY((transpose_pad<T, T>(tp.H1, D, Mw, D, ws.TB, nullptr, 0, 1, nullptr, st)));
-  HS_TRY(grad_weight<T>(ws.TA, ws.TB, D, D, Mwpad, g->w_p2, st));
+  HS_TRY(grad_weight<T>(ws.TA, ws.TB, D, D, Mwpad, g->w_p2, ws.DWP, st));
   {
     GemmEpilogue ep;   // dh1 = (d_out W2) o gelu'(h1)
     set_act_out(ep, ws.dH, D);
@@ -495,7 +517,7 @@ int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_
   HS_TRY((transpose_pad<T, T>(ws.dH, D, Mw, D, ws.TA, nullptr, 0, 0, g->b_p0 ? ws.CS : nullptr, st)));
   if (g->b_p0) HS_TRY(colsum_finish(ws.CS, Mwpad / 64, D, g->b_p0, st));
   HS_TRY((transpose_pad<T, T>(tp.A, kHidden, Mw, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-  HS_TRY(grad_weight<T>(ws.TA, ws.TB, D, kHidden, Mwpad, g->w_p0, st));
+  HS_TRY(grad_weight<T>(ws.TA, ws.TB, D, kHidden, Mwpad, g->w_p0, ws.DWP, st));
   {
     GemmEpilogue ep;   // dA = dh1 W_p0
     ep.out_f32 = ws.dF; ep.ld_f32 = kHidden;
@@ -510,7 +532,7 @@ int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_
   HS_TRY((transpose_pad<float, T>(ws.dQ, kHidden, Mw, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_o ? ws.CS : nullptr, st)));
   if (g->b_o) HS_TRY(colsum_finish(ws.CS, Mwpad / 64, kHidden, g->b_o, st));
   HS_TRY((transpose_pad<T, T>(tp.O, kHidden, Mw, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-  HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mwpad, g->w_o, st));
+  HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mwpad, g->w_o, ws.DWP, st));
   {
     GemmEpilogue ep;   // dO = dZ W_o
     set_act_out(ep, ws.dO, kHidden);
@@ -523,13 +545,13 @@ int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_
   HS_TRY((transpose_pad<float, T>(ws.dQ, kHidden, Mw, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_q ? ws.CS : nullptr, st)));
   if (g->b_q) HS_TRY(colsum_finish(ws.CS, Mwpad / 64, kHidden, g->b_q, st));
   HS_TRY((transpose_pad<T, T>(tp.LR, kHidden, Mw, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-  HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mwpad, g->w_q, st));
+  HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mwpad, g->w_q, ws.DWP, st));
   // Wk | Wv over the HR tokens
   HS_TRY((transpose_pad<T, T>(ws.dKV, 2 * kHidden, Mp, 2 * kHidden, ws.TA, nullptr, 0, 0, g->b_kv ? ws.CS : nullptr, st)));
   if (g->b_kv) HS_TRY(colsum_finish(ws.CS, Mppad / 64, 2 * kHidden, g->b_kv, st));
   if (g->w_kv) {
     HS_TRY((transpose_pad<T, T>(hr, kHidden, Mp, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
-    HS_TRY(grad_weight<T>(ws.TA, ws.TB, 2 * kHidden, kHidden, Mppad, g->w_kv, st));
+    HS_TRY(grad_weight<T>(ws.TA, ws.TB, 2 * kHidden, kHidden, Mppad, g->w_kv, ws.DWP, st));
   }
   if (d_hr != nullptr) {
     if (wt->w_kv_t == nullptr || wt->w_q_t == nullptr) return HS_ERR_ARG;

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hsenet_b200 import _lib  # noqa: E402
 
-PHASES = ["wait s_full + fence::after", "tcgen05.ld x2 + wait::ld", "fence + arrive s_free",
+PHASES = ["wait s_full (+ fence::after in tri/rowwarp)", "tcgen05.ld + wait::ld", "fence::after (split kernel only)",
           "row max + lazy-rescale test", "exp2 / sum / pack", "tcgen05.st P (issue)", "O-correction vote (+rare path)",
           "wait::st + fence + arrive p_full"]
 ISSUER = ["operand waits (v_full, k_full)", "wait p_full(t) + fence", "4 x P V mma + 2 commits", "4 x Q K^T mma + 2 commits"]
@@ -47,6 +47,8 @@ def main():
     assert fn(buf) == 0
     for title, base, names in (("softmax warp 2", 0, PHASES), ("MMA issuer, even steps", 16, ISSUER), ("MMA issuer, odd steps", 32, ISSUER)):
         n = buf[base + 15]
+        if n == 0:
+            continue
         print(f"B={B} S={S} {title}: {n} steps, loop {buf[base + 14]} cycles = {buf[base + 14] / n:.0f} per step")
         for i, name in enumerate(names):
             print(f"  {name:40s} {buf[base + i] / n:8.1f} cycles/step")

@@ -123,6 +123,7 @@ SIGNATURES = {
                                               C.c_size_t, vp]),
     "hsenet_packer_backward": (C.c_int, [C.POINTER(PackerWeights), C.POINTER(PackerWeightsT), vp, C.c_int, C.c_int, vp,
                                          vp, C.c_size_t, C.POINTER(PackerGrads), vp, vp, C.c_size_t, vp]),
+    "hsenet_self_attention_ws": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "hsenet_self_attention_train": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "hsenet_self_attention_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
 }

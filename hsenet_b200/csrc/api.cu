@@ -114,6 +114,7 @@ struct VitWs {
   T* S16;        // [B*32,768]   slice features as act
   float* SKV;    // [B*32,1536]  Wk|Wv of the slice features
   float2* STATS; // [2*kMaxFusedLayers, M]  (sum, sum of squares) per residual row for the LayerNorms folded into GEMMs
+  float* KMAX;   // [B*12]  largest squared key norm per (volume, head): scratch of the max-free attention softmax
   size_t stats_bytes;
   size_t total;
   VitWs(void* base, int B) {
@@ -128,6 +129,7 @@ struct VitWs {
     SKV = b.take<float>(static_cast<size_t>(B) * kNSlice * 2 * kHidden);
     stats_bytes = 2 * static_cast<size_t>(kMaxFusedLayers) * M * sizeof(float2);
     STATS = b.take<float2>(2 * static_cast<size_t>(kMaxFusedLayers) * M);
+    KMAX = b.take<float>(static_cast<size_t>(B) * kHeads);
     total = b.off;
   }
 };
@@ -239,7 +241,7 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
         HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
       }
     }
-    HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, nullptr, B, kSeq, st));
+    HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, nullptr, ws.KMAX, B, kSeq, st));
     {
       GemmEpilogue ep;   // out_proj + residual
       ep.bias = bw.b_out; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
@@ -505,7 +507,7 @@ int hsenet_self_attention(const void* qkv, void* out, int B, int S, int precisio
   if (qkv == nullptr || out == nullptr) return HSENET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == HSENET_PREC_BF16)
-    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), nullptr, B, S, st);
+    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), nullptr, nullptr, B, S, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), nullptr, B, S, st);
   return HSENET_ERR_ARG;

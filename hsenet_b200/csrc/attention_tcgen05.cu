@@ -461,6 +461,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
 }
 
 
+// Largest squared key norm per (volume, head): kmax2[b*12 + h] = max_k |K[b,k,h,:]|^2 (non-negative floats compare like
+// their bit patterns, so an integer atomicMax is exact and order-independent).  Feeds the max-free softmax below.
+__global__ void __launch_bounds__(192) attn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, int* __restrict__ kmax_bits,
+                                                        int S) {
+  __shared__ float red[16][kHeads];
+  const int h = threadIdx.x, ry = threadIdx.y, b = blockIdx.y;
+  const int r = blockIdx.x * 16 + ry;
+  float n2 = 0.f;
+  if (r < S) {
+    const uint4* p = reinterpret_cast<const uint4*>(qkv + (static_cast<long>(b) * S + r) * (3 * kHidden) + kHidden + h * kHeadDim);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 u = __ldg(p + j);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+        n2 = fmaf(f.x, f.x, fmaf(f.y, f.y, n2));
+      }
+    }
+  }
+  red[ry][h] = n2;
+  __syncthreads();
+  if (ry == 0) {
+    float m = red[0][h];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, red[i][h]);
+    atomicMax(kmax_bits + b * kHeads + h, __float_as_int(m));
+  }
+}
+
 // =====================================================================================================================
 // Key-split variant (default since round 2): EIGHT softmax warps per CTA, two per TMEM lane quarter.  The two warps of a
 // quarter share the same 32 query rows and split every 64-key step by KEY half (keys 0..31 / 32..63): each keeps its own
@@ -483,7 +514,7 @@ constexpr int ATS_SMEM = ATT_SMEM + 2 * 128 * 8;
 template <int POLY>
 __global__ void __launch_bounds__(ATS_THREADS, 2)
 attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
-                       float* __restrict__ lse_out, int S) {
+                       float* __restrict__ lse_out, const float* __restrict__ kmax2, int S) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -663,9 +694,35 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     const uint32_t col_o = ATS_COL_O + half * kHeadDim;
     float m = -INFINITY;
     float l = 0.f;
+    // MAX-FREE mode.  By Cauchy-Schwarz every scaled score of this row is <= mhat = c |q| max_k |k|, so mhat can replace the
+    // running maximum: P = 2^(s c - mhat) never overflows, the row sum / output ratio is unchanged, and the per-step row
+    // maximum (0.8 of ~4.5 instructions per score), the lazy-rescale test, the warp vote and the O correction all vanish.
+    // bf16 / fp32 carry an 8-bit exponent, so a loose bound costs no precision as long as nothing underflows: the worst
+    // case is a score of -mhat (q anti-aligned with a key), i.e. P = 2^(-2 mhat), hence the mode is only taken when
+    // mhat <= 50 for every row of the warp (true for LayerNorm'ed activations; otherwise the exact online softmax runs).
+    bool bounded = false;
+    if (kmax2 != nullptr) {
+      smx_wait(&bars->q_full, 0);
+      const uint4* qrow = reinterpret_cast<const uint4*>(sQ + (quarter * 32 + lane) * 128);   // swizzle permutes chunks only
+      float q2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 u = qrow[j];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+          q2 = fmaf(f.x, f.x, fmaf(f.y, f.y, q2));
+        }
+      }
+      const float mhat = c * sqrtf(q2 * __ldg(kmax2 + b * kHeads + h)) * 1.0001f;
+      bounded = !__any_sync(0xffffffffu, !(mhat <= 50.0f));
+      if (bounded) m = mhat;
+    }
     if constexpr (kEarlyProbe) ATT_PROBE_DECL;
     ATT_TR_DECL;
-    auto softmax_step = [&](const int t, auto masked) {
+    auto softmax_step = [&](const int t, auto masked, auto maxfree) {
+      constexpr bool MAXFREE = decltype(maxfree)::value;
       const int bsel = t & 1;
       const uint32_t col_s = ATS_COL_S + bsel * KS + half * 32;
       if constexpr (kEarlyProbe) {
@@ -691,24 +748,26 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
           for (int i = 0; i < 32; ++i)
             if (kbase + i >= S) x[i] = 0xff800000u;
         }
-        float mx[4];
+        if constexpr (!MAXFREE) {
+          float mx[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mx[u] = __uint_as_float(x[u]);
+          for (int u = 0; u < 4; ++u) mx[u] = __uint_as_float(x[u]);
 #pragma unroll
-        for (int i = 4; i < 32; i += 4) {
+          for (int i = 4; i < 32; i += 4) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(x[i + u]));
-        }
-        const float tm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
-        if (tm > m + 8.0f) {
-          alpha = ex2(m - tm);
-          m = tm;
+            for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(x[i + u]));
+          }
+          const float tm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
+          if (tm > m + 8.0f) {
+            alpha = ex2(m - tm);
+            m = tm;
+          }
         }
         ATT_TR(3);
         // a half that has not seen a valid key yet (only possible in a masked step) keeps m = -inf: subtract 0 instead,
         // so that the all -inf scores give exp2(-inf) = 0 and not exp2(-inf + inf)
         float msub = m;
-        if constexpr (decltype(masked)::value) msub = (m == -INFINITY) ? 0.f : m;
+        if constexpr (decltype(masked)::value && !MAXFREE) msub = (m == -INFINITY) ? 0.f : m;
         const uint64_t c2 = pack2(c, c), nm2 = pack2(-msub, -msub);
         uint64_t rs2 = pack2(0.f, 0.f);
 #pragma unroll
@@ -729,7 +788,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         }
         float rs0, rs1;
         unpack2(rs2, rs0, rs1);
-        l = l * alpha + (rs0 + rs1);
+        if constexpr (MAXFREE) l += rs0 + rs1; else l = l * alpha + (rs0 + rs1);
         ATT_TR(4);
         tmem_st16(tmem_base + lane_base + col_s, pk);
         ATT_TR(5);
@@ -738,7 +797,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         if (t + 1 < nsub) att_probe_issue(&bars->s_full[bsel ^ 1], ((t + 1) >> 1) & 1);
         else att_probe_clear();
       }
-      if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+      if (!MAXFREE && t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         smx_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
         if (t >= 2) smx_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
         tc_fence_after();
@@ -761,8 +820,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       ATT_TR(7);
     };
     const bool ragged = (S % KS) != 0;
-    for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{});
-    if (ragged) softmax_step(nsub - 1, std::true_type{});
+    if (bounded) {
+      for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{}, std::true_type{});
+      if (ragged) softmax_step(nsub - 1, std::true_type{}, std::true_type{});
+    } else {
+      for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{}, std::false_type{});
+      if (ragged) softmax_step(nsub - 1, std::true_type{}, std::false_type{});
+    }
     if (warp == HSENET_ATT_TRACE_WARP && lane == 0) { ATT_TR_DUMP(0); }
     // ---- merge the two key halves and store: this warp takes output columns [half*32, half*32+32) of its 32 rows ----
     ml[half * 128 + quarter * 32 + lane] = make_float2(m, l);
@@ -813,7 +877,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
 
 }  // namespace
 
-int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int S, cudaStream_t stream) {
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, float* kmax_scratch, int B, int S,
+                   cudaStream_t stream) {
   if (B <= 0 || S <= 0) return HS_OK;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return HS_ERR_ALIGN;
   CUtensorMap tm;
@@ -844,9 +909,23 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int
   const bool tri = kv != nullptr && kv[0] == 't';
   const dim3 grid((S + QT - 1) / QT, kHeads, B);
   if (split) {
-    if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);
-    else if (poly >= 2) launch_pdl(attention_split_kernel<2>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);
-    else launch_pdl(attention_split_kernel<0>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, S);
+    // Max-free softmax (OPT-IN, HSENET_ATT_MAXFREE=1): needs the largest key norm per (volume, head), a small pre-pass over K
+    // into the caller's scratch.  Measured on B200: it removes 26 % of the softmax warps' instructions (row max, rescale
+    // test, vote, O correction) and the kernel is NOT faster (148.0 -> 155.8 us at batch 8 with the pre-pass, equal without
+    // it) -- the step time is not set by the softmax instruction stream (profiles/README.md) -- so the exact online softmax
+    // stays the default.
+    const char* mf = std::getenv("HSENET_ATT_MAXFREE");
+    const float* kmax = nullptr;
+    if (kmax_scratch != nullptr && mf != nullptr && mf[0] == '1') {
+      if (cudaMemsetAsync(kmax_scratch, 0, static_cast<size_t>(B) * kHeads * sizeof(float), stream) != cudaSuccess)
+        return HS_ERR_CUDA;
+      attn_kmax_kernel<<<dim3((S + 15) / 16, B), dim3(kHeads, 16), 0, stream>>>(qkv, reinterpret_cast<int*>(kmax_scratch), S);
+      count_launch();
+      kmax = kmax_scratch;
+    }
+    if (poly >= 4) launch_pdl(attention_split_kernel<4>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, kmax, S);
+    else if (poly >= 2) launch_pdl(attention_split_kernel<2>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, kmax, S);
+    else launch_pdl(attention_split_kernel<0>, grid, dim3(ATS_THREADS), ATS_SMEM, stream, tm, out, lse, kmax, S);
   } else if (tri) {
     if (poly >= 4) launch_pdl(attention_kernel<4, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);
     else if (poly >= 2) launch_pdl(attention_kernel<2, 3>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, out, lse, S);

@@ -30,8 +30,9 @@ struct Prec<__nv_bfloat16> {
                   cudaStream_t s) {
     return gemm_bf16(A, lda, W, ldw, M, N, K, ep, s);
   }
-  static int attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int S, cudaStream_t s) {
-    return attention_bf16(qkv, out, lse, B, S, s);
+  static int attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, float* kmax, int B, int S,
+                       cudaStream_t s) {
+    return attention_bf16(qkv, out, lse, kmax, B, S, s);
   }
   static int attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* d_out,
                            const float* lse, float* dvec, __nv_bfloat16* d_qkv, int B, int S, cudaStream_t s) {
@@ -44,7 +45,7 @@ struct Prec<float> {
                   cudaStream_t s) {
     return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, M, N, K, ep, s);
   }
-  static int attention(const float* qkv, float* out, float* lse, int B, int S, cudaStream_t s) {
+  static int attention(const float* qkv, float* out, float* lse, float* /*kmax*/, int B, int S, cudaStream_t s) {
     return attention_f32(qkv, out, lse, B, S, s);
   }
   static int attention_bwd(const float* qkv, const float* out, const float* d_out, const float* lse, float* dvec,

@@ -105,7 +105,10 @@ int patch_embed_tf32(const float* images, const float* w_stack, int B, int n_tow
 // qkv [B*S, 2304] with feature order (qkv, head, d); out [B*S, 768] heads concatenated.
 // lse (optional, training forward): [B, 12, S_pad] fp32 with S_pad = ceil(S/128)*128, log2-domain log-sum-exp of the scaled
 // scores (m + log2 l); entries S <= q < S_pad are written as +inf.
-int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, int B, int S, cudaStream_t stream);
+// kmax_scratch (optional): fp32 [B*12]; when given, a pre-pass stores the largest squared key norm per (volume, head) there and
+// the kernel runs its max-free softmax (attention_tcgen05.cu) where the Cauchy-Schwarz bound allows it.
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, float* kmax_scratch, int B, int S,
+                   cudaStream_t stream);
 int attention_f32(const float* qkv, float* out, float* lse, int B, int S, cudaStream_t stream);
 // Backward of the fused attention (recompute style: P is rebuilt from qkv and lse).  d_out [B*S,768] (gradient of the
 // re-concatenated heads), out [B*S,768] (the forward result) -> d_qkv [B*S,2304].  dvec: scratch [B,12,S_pad] fp32.

@@ -20,6 +20,7 @@ struct TrunkWs {
   T* QKV;       // [M,2304]
   T* ATT;       // [M,768]
   T* H;         // [M,3072]  (also the patch matrix [B*32*196,256])
+  float* KMAX;  // [B*32*12] key-norm scratch of the max-free attention softmax
   size_t total;
   TrunkWs(void* base, int B) {
     const size_t M = static_cast<size_t>(B) * kNSlice * kTrunkSeq;
@@ -29,6 +30,7 @@ struct TrunkWs {
     QKV = b.take<T>(M * 3 * kHidden);
     ATT = b.take<T>(M * kHidden);
     H = b.take<T>(M * kMlp);
+    KMAX = b.take<float>(static_cast<size_t>(B) * kNSlice * kHeads);
     total = b.off;
   }
 };
@@ -59,7 +61,7 @@ int slice_trunk_forward(const hsenet_trunk_weights* w, const float* images, int 
       set_act_out(ep, ws.QKV, 3 * kHidden);
       HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
     }
-    HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, nullptr, NS, kTrunkSeq, st));
+    HS_TRY(Prec<T>::attention(ws.QKV, ws.ATT, nullptr, ws.KMAX, NS, kTrunkSeq, st));
     {
       GemmEpilogue ep;
       ep.bias = bw.b_out; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;

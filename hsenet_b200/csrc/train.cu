@@ -204,7 +204,7 @@ int vit_forward_train(const hsenet_vit_weights* w, const float* images, const fl
       set_act_out(ep, tp.QKV[l], 3 * kHidden);
       HS_TRY(Prec<T>::gemm(tp.XN1[l], kHidden, bw.w_qkv, kHidden, M, 3 * kHidden, kHidden, ep, st));
     }
-    HS_TRY(Prec<T>::attention(tp.QKV[l], tp.ATT[l], tp.LSE[l], B, kSeq, st));
+    HS_TRY(Prec<T>::attention(tp.QKV[l], tp.ATT[l], tp.LSE[l], ws.DVEC, B, kSeq, st));   // DVEC doubles as key-norm scratch
     {
       GemmEpilogue ep;
       ep.bias = bw.b_out; ep.resid = tp.X[2 * l]; ep.ld_resid = kHidden; ep.out_f32 = tp.X[2 * l + 1]; ep.ld_f32 = kHidden;
@@ -712,12 +712,23 @@ int hsenet_packer_backward(const hsenet_packer_weights* w, const hsenet_packer_w
   return HSENET_ERR_ARG;
 }
 
+int hsenet_self_attention_ws(const void* qkv, void* out, float* lse, float* scratch, int B, int S, int precision,
+                             hsenet_stream_t stream) {
+  if (qkv == nullptr || out == nullptr) return HSENET_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == HSENET_PREC_BF16)
+    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, scratch, B, S, st);
+  if (precision == HSENET_PREC_FP32_VERIFY)
+    return attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), lse, B, S, st);
+  return HSENET_ERR_ARG;
+}
+
 int hsenet_self_attention_train(const void* qkv, void* out, float* lse, int B, int S, int precision,
                                 hsenet_stream_t stream) {
   if (qkv == nullptr || out == nullptr || lse == nullptr) return HSENET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == HSENET_PREC_BF16)
-    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, S, st);
+    return attention_bf16(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, nullptr, B, S, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), lse, B, S, st);
   return HSENET_ERR_ARG;

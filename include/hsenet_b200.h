@@ -343,6 +343,13 @@ int hsenet_slice_trunk_forward(const hsenet_trunk_weights* w, const float* image
 
 /* Operator-level: backward of hsenet_self_attention.  lse / dvec: fp32 [B,12,ceil(S/128)*128]; lse comes from
  * hsenet_self_attention_train. */
+/* hsenet_self_attention with optional outputs / scratch: lse (optional, fp32 [B,12,ceil(S/128)*128]) and scratch (optional,
+ * fp32 [B*12]).  With scratch AND the environment switch HSENET_ATT_MAXFREE=1 the bf16 kernel runs its max-free softmax: a
+ * pre-pass stores the largest key norm per (volume, head) there and exp2(s - c |q| max|k|) replaces the running-maximum
+ * bookkeeping wherever that bound is <= 50 (log2 units); rows with a looser bound take the exact online softmax.  Results
+ * differ from the exact path only by fp32 rounding.  (Opt-in: measured not faster on B200.) */
+int hsenet_self_attention_ws(const void* qkv, void* out, float* lse, float* scratch, int B, int S, int precision,
+                             hsenet_stream_t stream);
 int hsenet_self_attention_train(const void* qkv, void* out, float* lse, int B, int S, int precision,
                                 hsenet_stream_t stream);
 int hsenet_self_attention_backward(const void* qkv, const void* out, const void* d_out, const float* lse, float* dvec,

@@ -176,6 +176,40 @@ def test_attention_bf16(lib, cuda, B, S, scale, kernel, monkeypatch):
     assert m["cos"] > 0.9995 and m["max_rel"] < 1.5e-2, m
 
 
+# Max-free softmax (scratch given): scale 0.4 keeps c |q| max|k| below the threshold (bounded mode), 1.0 mixes rows, 4.0
+# forces the exact fallback everywhere; anti-aligned and zero keys probe the underflow margin of the bound
+@pytest.mark.parametrize("B,S,scale", [(2, 2049, 0.4), (2, 2049, 1.0), (1, 2049, 4.0), (3, 197, 0.5), (2, 130, 0.3),
+                                       (1, 1, 0.5), (2, 33, 0.6), (1, 2050, 0.45)])
+def test_attention_bf16_maxfree(lib, cuda, B, S, scale, monkeypatch):
+    from hsenet_b200 import _lib
+    monkeypatch.setenv("HSENET_ATT_MAXFREE", "1")        # opt-in mode (not faster on B200, kept with its tests)
+    g = torch.Generator().manual_seed(7 * S + B)
+    qkv = (torch.randn(B * S, 2304, generator=g) * scale)
+    if S >= 130:
+        qkv[5, 768:1536] = 0.0                                   # a zero key
+        qkv[7, 768:768 + 64] = -3.0 * qkv[9, 0:64]               # a key anti-aligned with query 9 of head 0
+    qkv = qkv.to(torch.bfloat16)
+    ref = _attn_ref(qkv, B, S)
+    qd = qkv.to(cuda)
+    out = torch.full((B * S, 768), float("nan"), dtype=torch.bfloat16, device=cuda)
+    out2 = torch.empty_like(out)
+    sp = (S + 127) // 128 * 128
+    lse = torch.empty(B, 12, sp, device=cuda)
+    scratch = torch.full((B * 12,), float("nan"), device=cuda)
+    _lib.check(lib.hsenet_self_attention_ws(qd.data_ptr(), out.data_ptr(), lse.data_ptr(), scratch.data_ptr(), B, S, 0,
+                                            _st()), "attention_ws")
+    _lib.check(lib.hsenet_self_attention(qd.data_ptr(), out2.data_ptr(), B, S, 0, _st()), "attention")
+    torch.cuda.synchronize()
+    kn = qkv.float().reshape(B, S, 3, 12, 64)[:, :, 1].square().sum(-1).amax(dim=1).reshape(-1)       # max_k |k|^2 per (b,h)
+    assert torch.allclose(scratch.cpu(), kn, rtol=1e-5)
+    m = metrics(out, ref)
+    assert m["cos"] > 0.9995 and m["max_rel"] < 1.5e-2, m
+    assert metrics(out, out2.float().cpu())["max_rel"] < 1.5e-2                # max-free vs exact online softmax
+    q, k, _ = qkv.float().reshape(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    ref_lse = torch.logsumexp(q @ k.transpose(-1, -2) * 0.125, dim=-1) * 1.4426950408889634
+    assert torch.allclose(lse[:, :, :S].cpu(), ref_lse, atol=2e-2, rtol=0)
+
+
 @pytest.mark.parametrize("B,S", [(1, 2049), (2, 130)])
 def test_attention_f32(lib, cuda, B, S):
     from hsenet_b200 import _lib

@@ -21,13 +21,21 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--seq", type=int, default=2049)
+    ap.add_argument("--ws", action="store_true", help="give the kernel key-norm scratch (max-free softmax where the bound allows)")
+    ap.add_argument("--scale", type=float, default=1.0, help="std of the random qkv activations")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
     st = torch.cuda.current_stream(dev).cuda_stream
     S = args.seq
     for B in [int(b) for b in args.batches.split(",")]:
-        qkv = (torch.randn(B * S, 2304, device=dev)).to(torch.bfloat16)
+        qkv = (torch.randn(B * S, 2304, device=dev) * args.scale).to(torch.bfloat16)
+        scratch = torch.empty(B * 12, device=dev)
+
+        def call():
+            if args.ws:
+                return lib.hsenet_self_attention_ws(qkv.data_ptr(), out.data_ptr(), None, scratch.data_ptr(), B, S, 0, st)
+            return lib.hsenet_self_attention(qkv.data_ptr(), out.data_ptr(), B, S, 0, st)
         out = torch.empty(B * S, 768, dtype=torch.bfloat16, device=dev)
         fl = 4.0 * B * 12 * S * S * 64
         for mode in args.modes.split(","):
@@ -35,11 +43,11 @@ def main():
             res = []
             for _ in range(args.reps):
                 for _ in range(5):
-                    lib.hsenet_self_attention(qkv.data_ptr(), out.data_ptr(), B, S, 0, st)
+                    call()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(args.iters):
-                    lib.hsenet_self_attention(qkv.data_ptr(), out.data_ptr(), B, S, 0, st)
+                    call()
                 e1.record()
                 torch.cuda.synchronize()
                 res.append(e0.elapsed_time(e1) * 1e3 / args.iters)

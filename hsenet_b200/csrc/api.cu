@@ -100,7 +100,7 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64
 
 namespace {
 
-constexpr int kMaxFusedLayers = 32;    // statistics slots in the workspace; deeper layers keep the LayerNorm kernel
+constexpr int kStatSlots = kHidden / 128;   // column slabs of a residual row: one partial-statistics slot each
 constexpr float kLnEps = 1e-5f;        // nn.LayerNorm default (same constant as layernorm_rows)
 
 // ---- ViT workspace layout -----------------------------------------------------------------------------------
@@ -113,7 +113,8 @@ struct VitWs {
   T* H;          // [M,3072]  (aliased by the im2col patches [Mp,1024] and, stage 2, XP fp32 [Mp,768])
   T* S16;        // [B*32,768]   slice features as act
   float* SKV;    // [B*32,1536]  Wk|Wv of the slice features
-  float2* STATS; // [2*kMaxFusedLayers, M]  (sum, sum of squares) per residual row for the LayerNorms folded into GEMMs
+  float2* STATS; // [2, 6, M]  per-128-column partial (sum, sum of squares) of the residual rows entering norm1 / norm2, for
+                 //   the LayerNorms folded into GEMMs (rewritten by every producing GEMM: no clearing, no atomics)
   float* KMAX;   // [B*12]  largest squared key norm per (volume, head): scratch of the max-free attention softmax
   size_t stats_bytes;
   size_t total;
@@ -127,8 +128,8 @@ struct VitWs {
     H = b.take<T>(M * kMlp);
     S16 = b.take<T>(static_cast<size_t>(B) * kNSlice * kHidden);
     SKV = b.take<float>(static_cast<size_t>(B) * kNSlice * 2 * kHidden);
-    stats_bytes = 2 * static_cast<size_t>(kMaxFusedLayers) * M * sizeof(float2);
-    STATS = b.take<float2>(2 * static_cast<size_t>(kMaxFusedLayers) * M);
+    stats_bytes = 2 * static_cast<size_t>(kStatSlots) * M * sizeof(float2);
+    STATS = b.take<float2>(2 * static_cast<size_t>(kStatSlots) * M);
     KMAX = b.take<float>(static_cast<size_t>(B) * kHeads);
     total = b.off;
   }
@@ -214,25 +215,22 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
   // statistics, the consuming GEMM runs on XN with W' = gamma (.) W and normalises in its epilogue.
   constexpr bool kCanFold = std::is_same<T, __nv_bfloat16>::value;
   auto folds_ln1 = [&](int l) {
-    return kCanFold && l >= 1 && l < w->num_layers && l < kMaxFusedLayers && w->blocks_host[l].w_qkv_ln != nullptr &&
+    return kCanFold && l >= 1 && l < w->num_layers && w->blocks_host[l].w_qkv_ln != nullptr &&
            w->blocks_host[l].cs_qkv != nullptr && w->blocks_host[l].b_qkv_ln != nullptr;   // selected by the caller
   };
   auto folds_ln2 = [&](int l) {
-    return kCanFold && l < kMaxFusedLayers && w->blocks_host[l].w_fc1_ln != nullptr &&
+    return kCanFold && w->blocks_host[l].w_fc1_ln != nullptr &&
            w->blocks_host[l].cs_fc1 != nullptr && w->blocks_host[l].b_fc1_ln != nullptr;
   };
-  bool any_fold = false;
-  for (int l = 0; l < w->num_layers; ++l) any_fold |= folds_ln1(l) || folds_ln2(l);
-  if (any_fold && cudaMemsetAsync(ws.STATS, 0, ws.stats_bytes, st) != cudaSuccess) return HS_ERR_CUDA;
+  float2* const stats1 = ws.STATS;                                        // rows entering norm1 of the next layer
+  float2* const stats2 = ws.STATS + static_cast<size_t>(kStatSlots) * M;  // rows entering norm2 of this layer
   for (int l = 0; l < w->num_layers; ++l) {
     const hsenet_block_weights& bw = w->blocks_host[l];
-    float2* stats1 = ws.STATS + static_cast<size_t>(2 * l) * M;          // rows entering norm1 of layer l
-    float2* stats2 = ws.STATS + static_cast<size_t>(2 * l + 1) * M;      // rows entering norm2 of layer l
     {
       GemmEpilogue ep;   // qkv, no bias
       set_act_out(ep, ws.QKV, 3 * kHidden);
       if (folds_ln1(l)) {
-        ep.bias = bw.b_qkv_ln; ep.colsum = bw.cs_qkv; ep.stats_in = stats1;
+        ep.bias = bw.b_qkv_ln; ep.colsum = bw.cs_qkv; ep.stats_in = stats1; ep.ld_stats = M; ep.stats_slots = kStatSlots;
         ep.ln_inv_dim = 1.0f / kHidden; ep.ln_eps = kLnEps;
         HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_qkv_ln, kHidden, M, 3 * kHidden, kHidden, ep, st));
       } else {
@@ -247,7 +245,7 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
       ep.bias = bw.b_out; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
       if (folds_ln2(l)) {
         set_act_out(ep, ws.XN, kHidden);
-        ep.stats_out = stats2;
+        ep.stats_out = stats2; ep.ld_stats = M;
       }
       HS_TRY(Prec<T>::gemm(ws.ATT, kHidden, bw.w_out, kHidden, M, kHidden, kHidden, ep, st));
     }
@@ -256,7 +254,7 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
       ep.gelu = 1;
       set_act_out(ep, ws.H, kMlp);
       if (folds_ln2(l)) {
-        ep.bias = bw.b_fc1_ln; ep.colsum = bw.cs_fc1; ep.stats_in = stats2;
+        ep.bias = bw.b_fc1_ln; ep.colsum = bw.cs_fc1; ep.stats_in = stats2; ep.ld_stats = M; ep.stats_slots = kStatSlots;
         ep.ln_inv_dim = 1.0f / kHidden; ep.ln_eps = kLnEps;
         HS_TRY(Prec<T>::gemm(ws.XN, kHidden, bw.w_fc1_ln, kHidden, M, kMlp, kHidden, ep, st));
       } else {
@@ -270,7 +268,7 @@ int vit_forward(const hsenet_vit_weights* w, const float* images, const float* i
       ep.bias = bw.b_fc2; ep.resid = ws.X; ep.ld_resid = kHidden; ep.out_f32 = ws.X; ep.ld_f32 = kHidden;
       if (folds_ln1(l + 1)) {
         set_act_out(ep, ws.XN, kHidden);
-        ep.stats_out = ws.STATS + static_cast<size_t>(2 * (l + 1)) * M;
+        ep.stats_out = stats1; ep.ld_stats = M;
       }
       HS_TRY(Prec<T>::gemm(ws.H, kMlp, bw.w_fc2, kMlp, M, kHidden, kMlp, ep, st));
     }

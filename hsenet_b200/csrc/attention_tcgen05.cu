@@ -37,8 +37,14 @@ namespace {
 constexpr int QT = 128;                    // queries per CTA
 constexpr int KT = 128;                    // keys per TMA tile
 constexpr int KS = 64;                     // keys per softmax / MMA step
-constexpr int K_STAGES = 3;
-constexpr int V_STAGES = 2;
+#ifndef HSENET_ATT_K_STAGES
+#define HSENET_ATT_K_STAGES 3
+#endif
+#ifndef HSENET_ATT_V_STAGES
+#define HSENET_ATT_V_STAGES 2
+#endif
+constexpr int K_STAGES = HSENET_ATT_K_STAGES;
+constexpr int V_STAGES = HSENET_ATT_V_STAGES;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int SUB_BYTES = KS * 128;        // 64 rows x 128 B
 constexpr int ATT_THREADS = 224;   // producer warp, two MMA-issuing warps, four softmax warps
@@ -57,6 +63,11 @@ constexpr bool kSingleIssuer = HSENET_ATT_SINGLE_ISSUER != 0;
 #define HSENET_ATT_PV_INTERLEAVE 1
 #endif
 constexpr bool kPvInterleave = HSENET_ATT_PV_INTERLEAVE != 0;
+// Split kernel: wait for / publish the P store of step t only after the score load of step t+1 has been issued.
+#ifndef HSENET_ATT_DEFER_ST
+#define HSENET_ATT_DEFER_ST 0
+#endif
+constexpr bool kDeferSt = HSENET_ATT_DEFER_ST != 0;
 #ifndef HSENET_ATT_PARK
 #define HSENET_ATT_PARK 1
 #endif
@@ -111,14 +122,17 @@ __device__ unsigned long long g_att_trace[48];   // [0,16) softmax warp 2, [16,3
     g_att_trace[(base) + 14] = clock64() - tstart;                                     \
     g_att_trace[(base) + 15] = nsub;                                                   \
   }
-__device__ long long g_att_times[12][48];         // rows 0..7: p_full arrive of softmax warp r; 8: s_full seen (warp 3); 9: issuer woken; 10: issue end
+__device__ long long g_att_times[12][48];         // rows 0..7: p_full arrive of softmax warp r; 8: s_full seen (warp 3); 9: issuer woken; 10: issue end; 11: issuer has its K/V operands
 #define ATT_TS(row, step)                                                                          \
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (step) < 48) g_att_times[row][step] = clock64()
+#define ATT_TV(row, step, val)                                                                     \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_att_times[row][step] = (val)
 #else
 #define ATT_TR(i)
 #define ATT_TR_DECL
 #define ATT_TR_DUMP(base)
 #define ATT_TS(row, step)
+#define ATT_TV(row, step, val)
 #endif
 
 __device__ __forceinline__ float ex2(float x) {
@@ -507,7 +521,20 @@ __global__ void __launch_bounds__(192) attn_kmax_kernel(const __nv_bfloat16* __r
 // orders the overwrite), which keeps the CTA at 256 TMEM columns and two CTAs per SM:
 //     TMEM columns   0.. 63  S0 (P0_A at 0..15, P0_B at 32..47)    64..127  S1 (P1_A, P1_B)    128..191 O_A    192..255 O_B
 // Issuing threads, TMA rings and the step-parity protocol are those of the kernel above; p_full counts 8 warps.
-constexpr int ATS_THREADS = 352;   // producer warp, two MMA-issuing warps, eight softmax warps
+constexpr int ATS_THREADS = 384;   // four control warps (one per scheduler: producer / issuer by SM slot), eight softmax warps
+// The two CTAs that share an SM put their control warps on DIFFERENT schedulers (slot 0: producer warp 0, issuer warp 1;
+// slot 1: producer warp 2, issuer warp 3).  tools/attn_timeline.py: the two softmax warps that share a scheduler with
+// their CTA's issuing warp arrive 600-700 cycles after the other six at EVERY step (the lag follows the issuer when its
+// warp is moved), and p_full needs the slowest warp: the issue burst (8 tcgen05.mma + 4 commits, 350 cycles, held by the
+// tensor pipe's queue) starts exactly when those two warps begin their next step.  Spreading the two CTAs' issuers over
+// two schedulers does not remove that lag (each CTA still suffers from its own issuer) but measured +3 % at batch 32.
+#ifndef HSENET_ATT_SPREAD
+#define HSENET_ATT_SPREAD 1
+#endif
+// (Tried and removed: halving the commits per step -- K / V stages released once per 128-key tile, P V completion inferred
+// from s_full(t+1) -- made the kernel 3 % SLOWER and the issue burst longer, 350 -> 590 cycles: the issuing thread is held
+// by the tensor pipe's short queue, eight back-to-back MMAs block it longer than 4 + 4 with commits in between.)
+__device__ unsigned int g_att_sm_slots[1024];      // per SM: bit s set while a resident CTA holds slot s
 constexpr uint32_t ATS_COL_S = 0, ATS_COL_O = 128;
 constexpr int ATS_SMEM = ATT_SMEM + 2 * 128 * 8;
 
@@ -544,6 +571,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     }
     fence_mbar_init();
   }
+  __shared__ int s_slot;
+  unsigned int smid = 0;
+  if (threadIdx.x == 0) {
+    int slot = 0;
+    if (kSingleIssuer && HSENET_ATT_SPREAD) {
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      smid &= 1023u;
+      if (atomicOr(&g_att_sm_slots[smid], 1u) & 1u) {      // slot 0 taken by the co-resident CTA
+        atomicOr(&g_att_sm_slots[smid], 2u);
+        slot = 1;
+      }
+    }
+    s_slot = slot;
+  }
   if (warp == 1) {
     tmem_alloc(&bars->tmem_base, TMEM_COLS);
     tmem_relinquish();
@@ -552,6 +593,9 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+  const int slot = __shfl_sync(0xffffffffu, s_slot, 0);
+  const int producer_warp = 2 * slot, issuer_warp = 2 * slot + 1;
+  if (threadIdx.x == 0) { ATT_TV(11, 47, issuer_warp); }
   pdl_prologue_done();
 
   auto mma_issuer = [&](const int par) {
@@ -586,6 +630,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         ctl_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
         if (t2 < nsub) ctl_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
         ATT_TR(0);
+        if (lane == 0) { ATT_TS(11, t); }
         ctl_wait(&bars->p_full[sub], (t >> 1) & 1);
         if (lane == 0) { ATT_TS(9, t); }
         tc_fence_after();
@@ -650,7 +695,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     ATT_TR_DUMP(16 + 16 * par);
   };
 
-  if (warp == 0) {
+  if (warp == producer_warp) {
     // TMA producer (whole warp, elect-guarded issue; K one tile ahead of V -- see attention_kernel)
     if (elect_one()) {
       mbar_arrive_expect_tx(&bars->q_full, TILE_BYTES);
@@ -679,14 +724,14 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp == issuer_warp) {
     mma_issuer(0);
-  } else if (warp == 2) {
-    mma_issuer(1);        // returns at once in the single-issuer configuration
-  } else {
+  } else if (!kSingleIssuer && warp == 2) {
+    mma_issuer(1);        // two-issuer experiment (slot is always 0 there: producer warp 0, issuers 1 and 2)
+  } else if (warp >= 4) {
     // ===================== softmax warps: quarter = TMEM lane quarter (warp % 4), half = key half =====================
     const int quarter = warp & 3;
-    const int half = (warp - 3) >> 2;
+    const int half = (warp - 4) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const int qi = q0 + quarter * 32 + lane;
     const bool warp_live = (q0 + quarter * 32) < S;
@@ -731,13 +776,23 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
       }
       ATT_TR(0);
-      if (warp == 3 && lane == 0) { ATT_TS(8, t); }
+      if (warp == 4 && lane == 0) { ATT_TS(8, t); }
       tc_fence_after();
       ATT_TR(2);
       uint32_t x[32];
       uint32_t pk[16];
       float alpha = 1.f;
       if (warp_live) tmem_ld32(tmem_base + lane_base + col_s, x);
+      if constexpr (kDeferSt) {
+        // the previous step's P store is only now waited for and published: its latency hides behind this step's
+        // barrier wait and score load instead of sitting on the warp's serial path
+        if (t > 0) {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->p_full[bsel ^ 1]);
+        }
+      }
       // (two buffers: s_full(t+1) completes while this step's exponentials run, so the probe is issued after them)
       if (warp_live) {
         tmem_ld_wait();
@@ -812,11 +867,13 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         }
       }
       ATT_TR(6);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
-      if (lane == 0) { ATT_TS(warp - 3, t); }
+      if (!kDeferSt || t == nsub - 1) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
+      }
+      if (lane == 0) { ATT_TS(warp - 4, t); }
       ATT_TR(7);
     };
     const bool ragged = (S % KS) != 0;
@@ -827,7 +884,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       for (int t = 0; t < nsub - (ragged ? 1 : 0); ++t) softmax_step(t, std::false_type{}, std::false_type{});
       if (ragged) softmax_step(nsub - 1, std::true_type{}, std::false_type{});
     }
-    if (warp == HSENET_ATT_TRACE_WARP && lane == 0) { ATT_TR_DUMP(0); }
+    if (warp == 4 && lane == 0) { ATT_TR_DUMP(0); }
     // ---- merge the two key halves and store: this warp takes output columns [half*32, half*32+32) of its 32 rows ----
     ml[half * 128 + quarter * 32 + lane] = make_float2(m, l);
     asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 softmax warps only
@@ -873,6 +930,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0 && kSingleIssuer && HSENET_ATT_SPREAD) atomicAnd(&g_att_sm_slots[smid], ~(1u << slot));
 }
 
 }  // namespace

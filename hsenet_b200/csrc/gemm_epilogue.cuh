@@ -13,9 +13,12 @@
 // LayerNorm between two GEMMs is folded into their epilogues instead of running as a kernel of its own (which re-read
 // the fp32 residual stream, 50 MB per call at batch 8):  LN(x) W^T = rstd (x W'^T) - rstd mu colsum(W') + (W beta + b)
 // with W' = gamma (.) W, so
-//   EPI_F32_RESID_LN   the producer also writes a bf16 copy of its output rows (the next GEMM's A operand) and adds each
-//                      row's (sum, sum of squares) -- taken from the fp32 values -- into stats_out;
-//   EPI_BF16_LN, EPI_BF16_GELU_LN   the consumer multiplies by W' and applies the per-row scale / shift from stats_in.
+//   EPI_F32_RESID_LN   the producer also writes a bf16 copy of its output rows (the next GEMM's A operand) and stores each
+//                      row's (sum, sum of squares) over its 128-column slab -- taken from the fp32 values -- into the
+//                      slab's own slot stats_out[(col / 128) * ld_stats + row]: plain stores, no atomics, so the result is
+//                      bit-identical from run to run;
+//   EPI_BF16_LN, EPI_BF16_GELU_LN   the consumer multiplies by W' , adds the stats_slots (<= 8) partials of every row in a
+//                      fixed order and applies the per-row scale / shift.
 // All residual loads of a 32x32 block are issued before the first store (the residual aliases the output, so the
 // compiler cannot hoist them itself): this keeps the fp32 residual stream HBM-bound instead of latency-bound.
 #pragma once
@@ -41,6 +44,13 @@ __host__ inline int epilogue_mode(const GemmEpilogue& ep) {
     if (ep.out_bf16 == nullptr && ep.stats_out == nullptr) return EPI_F32_RESID;
   }
   return EPI_GENERIC;     // (does not implement the LayerNorm fields: callers must hit one of the cases above)
+}
+
+// LayerNorm-statistics fields a launcher must reject before it picks a kernel
+__host__ inline bool epilogue_stats_ok(const GemmEpilogue& ep, int N) {
+  if (ep.stats_out != nullptr && (N % 128 != 0 || N > 1024 || ep.ld_stats <= 0)) return false;
+  if (ep.stats_in != nullptr && (ep.stats_slots < 1 || ep.stats_slots > 8 || ep.ld_stats <= 0 || ep.colsum == nullptr)) return false;
+  return true;
 }
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7):
@@ -101,10 +111,11 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_ln_load(const GemmEpilogue& ep, int row_base, int M, int lane, float2 (&sq)[8]) {
   if constexpr (MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN) {
 #pragma unroll
+    // the 8 lanes that share a readback row each fetch ONE column-slab partial of it (slot = lane & 7)
     for (int it = 0; it < 8; ++it) {
       const int row = row_base + (lane >> 3) + 4 * it;
-      sq[it] = make_float2(0.f, 1.f);
-      if (row < M) sq[it] = __ldg(ep.stats_in + row);
+      sq[it] = make_float2(0.f, 0.f);
+      if (row < M && (lane & 7) < ep.stats_slots) sq[it] = ep.stats_in[static_cast<long>(lane & 7) * ep.ld_stats + row];
     }
   }
 }
@@ -114,8 +125,14 @@ __device__ __forceinline__ void epilogue_ln_coeffs(const GemmEpilogue& ep, const
   if constexpr (MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const float mean = sq[it].x * ep.ln_inv_dim;
-      const float var = fmaxf(sq[it].y * ep.ln_inv_dim - mean * mean, 0.f);
+      float sx = sq[it].x, sy = sq[it].y;        // butterfly over the 8 slot lanes: same bits on every lane, every run
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, d);
+        sy += __shfl_xor_sync(0xffffffffu, sy, d);
+      }
+      const float mean = sx * ep.ln_inv_dim;
+      const float var = fmaxf(sy * ep.ln_inv_dim - mean * mean, 0.f);
       ln_a[it] = rsqrtf(var + ep.ln_eps);
       ln_b[it] = -mean * ln_a[it];
     }
@@ -318,10 +335,7 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
       w2[i] = (b0 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, send, 1);
     }
     const int row = row_base + sub_row + 4 * (lane & 7);
-    if (row < M) {
-      atomicAdd(&ep.stats_out[row].x, w2[0]);
-      atomicAdd(&ep.stats_out[row].y, w2[1]);
-    }
+    if (row < M) ep.stats_out[static_cast<long>(col_base >> 7) * ep.ld_stats + row] = make_float2(w2[0], w2[1]);
   }
 }
 

@@ -298,6 +298,7 @@ int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, int M, int N,
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const int grid = 2 * pairs;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 2.0 * (double(M) * K + double(N) * K + double(M) * N), stream);
+  if (!epilogue_stats_ok(ep, N)) return HS_ERR_ARG;
   switch (epilogue_mode(ep)) {
     case EPI_BF16: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;
     case EPI_BF16_GELU: launch_pdl(gemm_bf16_2cta_kernel<EPI_BF16_GELU>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, ep, M, N, K, ksplit, kb_per, split_stride); break;

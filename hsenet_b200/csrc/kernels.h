@@ -40,8 +40,11 @@ struct GemmEpilogue {
   const void* dgelu_src = nullptr;
   int ld_dgelu = 0;
   // LayerNorm folded into the GEMMs on either side of it (gemm_epilogue.cuh):
-  float2* stats_out = nullptr;        // producer (EPI_F32_RESID): += (sum, sum of squares) of every output row
-  const float2* stats_in = nullptr;   // consumer (EPI_BF16[_GELU]): row statistics of the un-normalised A operand
+  float2* stats_out = nullptr;        // producer (EPI_F32_RESID): (sum, sum of squares) of every output row over each 128-
+                                      //   column slab, stored at [(col / 128) * ld_stats + row]  (N <= 1024)
+  const float2* stats_in = nullptr;   // consumer (EPI_BF16[_GELU]): those partials of the un-normalised A operand
+  long ld_stats = 0;                  // rows between two slab slots
+  int stats_slots = 0;                // consumer: slots to add per row (= producer N / 128, <= 8)
   const float* colsum = nullptr;      // consumer: sum_k W'[n,k] of the gain-folded weight
   float ln_inv_dim = 0.f;             // 1 / (row length the statistics were taken over)
   float ln_eps = 0.f;

@@ -29,10 +29,11 @@ buf = (C.c_longlong * 576)()
 assert fn(buf) == 0
 arr = [[buf[r * 48 + i] for i in range(48)] for r in range(12)]
 t0 = arr[8][2]
-print("step  s_full_seen | arrive of softmax warps 3..10 (relative to s_full_seen)             | last arrive -> issuer woken   issue   issue_end -> s_full(t+2)")
+print("CTA 0: issuing warp", arr[11][47], "(scheduler", arr[11][47] % 4, ")")
+print("step  s_full_seen | arrive of softmax warps 4..11 (scheduler = column % 4; rel. s_full_seen) | last arrive -> issuer woken   issue   issue_end -> s_full(t+2) | issuer: prev issue_end -> operands ready -> p_full seen")
 for t in range(2, 31):
     sf = arr[8][t]
     arrives = [arr[r][t] - sf for r in range(8)]
     last = max(arr[r][t] for r in range(8))
     iw, ie, nxt = arr[9][t], arr[10][t], arr[8][t + 2]
-    print(f"{t:4d} {sf - t0:11d} | " + " ".join(f"{a:6d}" for a in arrives) + f" | {iw - last:10d} {ie - iw:14d} {nxt - ie:10d}")
+    print(f"{t:4d} {sf - t0:11d} | " + " ".join(f"{a:6d}" for a in arrives) + f" | {iw - last:10d} {ie - iw:14d} {nxt - ie:10d} | {arr[11][t] - arr[10][t - 1]:8d} {iw - arr[11][t]:8d}")

@@ -534,6 +534,9 @@ constexpr int ATS_THREADS = 384;   // four control warps (one per scheduler: pro
 // (Tried and removed: halving the commits per step -- K / V stages released once per 128-key tile, P V completion inferred
 // from s_full(t+1) -- made the kernel 3 % SLOWER and the issue burst longer, 350 -> 590 cycles: the issuing thread is held
 // by the tensor pipe's short queue, eight back-to-back MMAs block it longer than 4 + 4 with commits in between.)
+// (Tried and removed: pacing the issuing thread between MMAs.  An 80-cycle clock spin after each MMA removes the lag of the
+// issuer's scheduler mates completely -- all eight softmax warps then arrive within 150 cycles of each other -- but the
+// issuer itself becomes the limit (950 cycles per step, 176 us); 20-55 cycle pauses change nothing, 146.8 us.)
 __device__ unsigned int g_att_sm_slots[1024];      // per SM: bit s set while a resident CTA holds slot s
 constexpr uint32_t ATS_COL_S = 0, ATS_COL_O = 128;
 constexpr int ATS_SMEM = ATT_SMEM + 2 * 128 * 8;

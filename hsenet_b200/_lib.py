@@ -67,6 +67,10 @@ class PackerWeightsT(C.Structure):
     _fields_ = [(n, vp) for n in ("w_q_t", "w_kv_t", "w_o_t", "w_p0_t", "w_p2_t")]
 
 
+class Dropout(C.Structure):
+    _fields_ = [("p_attn", C.c_float), ("p_out", C.c_float), ("seed_attn", C.c_ulonglong), ("seed_out", C.c_ulonglong)]
+
+
 class PackerGrads(C.Structure):
     _fields_ = [(n, vp) for n in ("w_q", "b_q", "w_kv", "b_kv", "w_o", "b_o", "ln_g", "ln_b", "w_p0", "b_p0", "w_p2", "b_p2")]
 
@@ -114,15 +118,17 @@ SIGNATURES = {
     "hsenet_vit_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "hsenet_vit_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hsenet_vit_forward_train": (C.c_int, [C.POINTER(VitWeights), vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t,
-                                           vp, C.c_size_t, vp]),
+                                           vp, C.c_size_t, C.POINTER(Dropout), vp]),
     "hsenet_vit_backward": (C.c_int, [C.POINTER(VitWeights), C.POINTER(VitWeightsT), vp, C.c_int, C.c_int, vp, vp, vp,
-                                      C.c_size_t, C.POINTER(VitGrads), vp, C.c_size_t, vp]),
+                                      C.c_size_t, C.POINTER(VitGrads), vp, C.c_size_t, C.POINTER(Dropout), vp]),
+    "hsenet_dropout_mask": (C.c_int, [C.c_float, C.c_ulonglong, C.c_longlong, vp, vp]),
     "hsenet_packer_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hsenet_packer_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hsenet_packer_forward_train": (C.c_int, [C.POINTER(PackerWeights), vp, C.c_int, C.c_int, vp, vp, C.c_size_t, vp,
-                                              C.c_size_t, vp]),
+                                              C.c_size_t, C.POINTER(Dropout), vp]),
     "hsenet_packer_backward": (C.c_int, [C.POINTER(PackerWeights), C.POINTER(PackerWeightsT), vp, C.c_int, C.c_int, vp,
-                                         vp, C.c_size_t, C.POINTER(PackerGrads), vp, vp, C.c_size_t, vp]),
+                                         vp, C.c_size_t, C.POINTER(PackerGrads), vp, vp, C.c_size_t, C.POINTER(Dropout),
+                                         vp]),
     "hsenet_self_attention_ws": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "hsenet_self_attention_train": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "hsenet_self_attention_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),

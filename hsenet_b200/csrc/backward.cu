@@ -305,7 +305,7 @@ __device__ __forceinline__ int window_member_b(int n, int e) {     // == rowops.
 template <typename T>
 __global__ void __launch_bounds__(256) window_attn_bwd_kernel(const T* __restrict__ dO, const float* __restrict__ Q,
                                                               const T* __restrict__ KV, float* __restrict__ dQ,
-                                                              T* __restrict__ dKV, long total) {
+                                                              T* __restrict__ dKV, long total, DropSpec dr) {
   const long w = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (w >= total) return;
   const int lane = threadIdx.x & 31;
@@ -339,9 +339,14 @@ __global__ void __launch_bounds__(256) window_attn_bwd_kernel(const T* __restric
 #pragma unroll
   for (int e = 0; e < 16; ++e) { sc[e] = expf(sc[e] - m); den += sc[e]; }
   const float inv = 1.0f / den;
+  // train-mode dropout: O = (p o M) V, so dP = M o (dO V^T) and dV uses the dropped probabilities; mk[e] = M_e (1 when off)
+  float mk[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e)
+    mk[e] = dr.on() ? drop_mask(dr.seed, dr.keep_thresh, dr.scale, static_cast<unsigned long long>(w) * 16 + e) : 1.0f;
   float pd = 0.f;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) { sc[e] *= inv; pd += sc[e] * dp[e]; }
+  for (int e = 0; e < 16; ++e) { sc[e] *= inv; dp[e] *= mk[e]; pd += sc[e] * dp[e]; }
   float4 dq[kVec];
 #pragma unroll
   for (int i = 0; i < kVec; ++i) dq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(256) window_attn_bwd_kernel(const T* __restric
     const T* kr = KV + tok * (2 * kHidden);
     T* dk = dKV + tok * (2 * kHidden);
     const float ds = sc[e] * (dp[e] - pd) * 0.036084391824351615f;
-    const float p = sc[e];
+    const float p = sc[e] * mk[e];
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(256) slice_xattn_bwd_rows_kernel(const float* 
                                                                    const float* __restrict__ KV,
                                                                    const T* __restrict__ dO, float* __restrict__ dQ,
                                                                    int accumulate, float* __restrict__ P,
-                                                                   float* __restrict__ dS, long total) {
+                                                                   float* __restrict__ dS, long total, DropSpec dr) {
   const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= total) return;
   const int lane = threadIdx.x & 31;
@@ -430,9 +435,13 @@ __global__ void __launch_bounds__(256) slice_xattn_bwd_rows_kernel(const float* 
   const float m = warp_max(sc);
   const float e = expf(sc - m);
   const float p = e / warp_sum(e);
+  // train-mode dropout: O = (p o M) V  ->  dP = M o (dO V^T); the key/value reduction below needs the DROPPED p for dV
+  const float mk = dr.on() ? drop_mask(dr.seed, dr.keep_thresh, dr.scale, static_cast<unsigned long long>(r) * kNSlice + lane)
+                           : 1.0f;
+  dp *= mk;
   const float pd = warp_sum(p * dp);
   const float ds = p * (dp - pd) * 0.036084391824351615f;
-  P[r * kNSlice + lane] = p;
+  P[r * kNSlice + lane] = p * mk;
   dS[r * kNSlice + lane] = ds;
   float4 acc[kVec];
 #pragma unroll
@@ -702,16 +711,16 @@ int attention_rowdot_f32(const float* out, const float* d_out, float* dvec, int 
 }
 
 template <typename T>
-int window_attn_bwd(const T* dO, const float* Q, const T* KV, float* dQ, T* dKV, int B, cudaStream_t st) {
+int window_attn_bwd(const T* dO, const float* Q, const T* KV, float* dQ, T* dKV, int B, cudaStream_t st, DropSpec dr) {
   const long total = static_cast<long>(B) * 128;
   if (total <= 0) return HS_OK;
-  window_attn_bwd_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(dO, Q, KV, dQ, dKV, total);
+  window_attn_bwd_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(dO, Q, KV, dQ, dKV, total, dr);
   count_launch();
   return launch_status();
 }
-template int window_attn_bwd<float>(const float*, const float*, const float*, float*, float*, int, cudaStream_t);
+template int window_attn_bwd<float>(const float*, const float*, const float*, float*, float*, int, cudaStream_t, DropSpec);
 template int window_attn_bwd<__nv_bfloat16>(const __nv_bfloat16*, const float*, const __nv_bfloat16*, float*,
-                                            __nv_bfloat16*, int, cudaStream_t);
+                                            __nv_bfloat16*, int, cudaStream_t, DropSpec);
 
 template <typename TG>
 int pool_bwd(const TG* dLR, float* dHR, int B, int accumulate, cudaStream_t st) {
@@ -726,20 +735,20 @@ template int pool_bwd<__nv_bfloat16>(const __nv_bfloat16*, float*, int, int, cud
 
 template <typename T>
 int slice_xattn_bwd(const float* Q, const float* KV, const T* dO, float* dQ, int accumulate, float* P, float* dS,
-                    float* dKV, int B, cudaStream_t st) {
+                    float* dKV, int B, cudaStream_t st, DropSpec dr) {
   const long total = static_cast<long>(B) * kNPatch;
   if (total <= 0) return HS_OK;
   slice_xattn_bwd_rows_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(Q, KV, dO, dQ, accumulate, P, dS,
-                                                                                       total);
+                                                                                       total, dr);
   count_launch();
   slice_xattn_bwd_kv_kernel<T><<<dim3(2 * kHidden / 256, B), 256, 0, st>>>(Q, dO, P, dS, dKV);
   count_launch();
   return launch_status();
 }
 template int slice_xattn_bwd<float>(const float*, const float*, const float*, float*, int, float*, float*, float*, int,
-                                    cudaStream_t);
+                                    cudaStream_t, DropSpec);
 template int slice_xattn_bwd<__nv_bfloat16>(const float*, const float*, const __nv_bfloat16*, float*, int, float*, float*,
-                                            float*, int, cudaStream_t);
+                                            float*, int, cudaStream_t, DropSpec);
 
 int score_scale_bwd(const float* dX, const float* XP, const float* Z, const float* g, const float* be, const float* ws,
                     const float* scores, float* dXP, float* dZ, float* dg_partial, float* db_partial,

@@ -292,6 +292,16 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   return r;
 }
 
+// Dropout keep-mask value of element idx (kernels.h DropSpec): scale when kept, 0 when dropped.  splitmix64 finaliser.
+__device__ __forceinline__ float drop_mask(unsigned long long seed, unsigned int keep_thresh, float scale,
+                                           unsigned long long idx) {
+  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<unsigned int>(z >> 32) < keep_thresh ? scale : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -145,8 +145,23 @@ int gather_rows(const void* in, int in_dtype, long batch_stride, long row_stride
 
 // ---- 2E3 slice-guided scoring (vit.py:332-345) ------------------------------------------------------------------
 // Q [B*2048,768] fp32 (projected query), KV [B*32,1536] fp32 (Wk|Wv of the slice features) -> O Act [B*2048,768]
+// Train-mode dropout of the two small attentions (vit.py:31-32,62 / spatial_pooling_projector.py:14-15,78): element `idx` of a
+// tensor is kept when the top 32 bits of splitmix64(seed + idx) are below keep_thresh and scaled by scale = 1 / (1 - p).
+// A counter-based mask: the backward kernels regenerate it from (seed, idx) instead of storing it.  scale == 0: disabled.
+struct DropSpec {
+  unsigned long long seed = 0;
+  unsigned int keep_thresh = 0;
+  float scale = 0.f;
+  __host__ __device__ bool on() const { return scale != 0.f; }
+};
+DropSpec make_dropspec(float p, unsigned long long seed);       // p <= 0: disabled
+// z[i] = resid[i] + mask(i) * z[i]  (dropout_2 in front of the residual add);  out[i] = mask(i) * in[i];  out[i] = mask(i)
+int dropout_residual(float* z, const float* resid, long n, DropSpec dr, cudaStream_t st);
+int dropout_scale(const float* in, float* out, long n, DropSpec dr, cudaStream_t st);
+int dropout_mask(float* out, long n, DropSpec dr, cudaStream_t st);
 template <typename OutT>
-int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn_opt, int B, cudaStream_t stream);
+int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn_opt, int B, cudaStream_t stream,
+                          DropSpec dr = DropSpec());
 // Z = Wq(x)+out_proj(...) [B*2048,768] fp32 -> LN -> . w_s + b_s -> sigmoid -> X[b,1+t,:] = XP[b,t,:] * score
 int score_and_scale(const float* Z, const float* ln_g, const float* ln_b, const float* w_s, const float* b_s,
                     const float* XP, float* X, float* scores_opt, int B, cudaStream_t stream);
@@ -156,7 +171,7 @@ template <typename T>
 int packer_pool(const T* HR, T* LR, int B, cudaStream_t stream);
 // Q [B*128,768] fp32; KV [B*2048,1536] Act (Wk|Wv of the HR tokens, natural token order) -> O Act [B*128,768]
 template <typename T>
-int packer_window_attention(const float* Q, const T* KV, T* O, int B, cudaStream_t stream);
+int packer_window_attention(const float* Q, const T* KV, T* O, int B, cudaStream_t stream, DropSpec dr = DropSpec());
 
 // ---- CLIP head (CLIP_stage1.py:100-101,117) ------------------------------------------------------------------------
 int l2_normalize_rows(const float* in, float* out, int rows, int dim, cudaStream_t stream);
@@ -182,12 +197,13 @@ template <typename T>
 int combine_final_grad(const T* d_tokens, const T* d_patch, int B, int seq, float* dy, cudaStream_t st);
 int sum_over_batch(const float* in, long batch_stride, int B, int rows, float* out, cudaStream_t st);
 template <typename T>
-int window_attn_bwd(const T* dO, const float* Q, const T* KV, float* dQ, T* dKV, int B, cudaStream_t st);
+int window_attn_bwd(const T* dO, const float* Q, const T* KV, float* dQ, T* dKV, int B, cudaStream_t st,
+                    DropSpec dr = DropSpec());
 template <typename TG>
 int pool_bwd(const TG* dLR, float* dHR, int B, int accumulate, cudaStream_t st);
 template <typename T>
 int slice_xattn_bwd(const float* Q, const float* KV, const T* dO, float* dQ, int accumulate, float* P, float* dS,
-                    float* dKV, int B, cudaStream_t st);
+                    float* dKV, int B, cudaStream_t st, DropSpec dr = DropSpec());
 int score_scale_bwd(const float* dX, const float* XP, const float* Z, const float* g, const float* be, const float* ws,
                     const float* scores, float* dXP, float* dZ, float* dg_partial, float* db_partial,
                     float* dws_partial, float* dbs_partial, int B, cudaStream_t st);

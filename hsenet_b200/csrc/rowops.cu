@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) packer_pool_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) packer_window_attn_kernel(const float* __restrict__ Q,
                                                                  const T* __restrict__ KV, T* __restrict__ O,
-                                                                 long total) {
+                                                                 long total, DropSpec dr) {
   const long w = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (w >= total) return;
   const int lane = threadIdx.x & 31;
@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(256) packer_window_attn_kernel(const float* __
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const T* vr = KV + (b * kNPatch + window_member(n, e)) * (2 * kHidden) + kHidden;
-    const float p = sc[e] * inv;
+    float p = sc[e] * inv;
+    if (dr.on()) p *= drop_mask(dr.seed, dr.keep_thresh, dr.scale, static_cast<unsigned long long>(w) * 16 + e);
 #pragma unroll
     for (int i = 0; i < kVecPerLane; ++i) {
       const float4 v = Vec4<T>::load(vr + (i * 32 + lane) * 4);
@@ -256,7 +257,7 @@ constexpr int kXaRowsPerCta = 128;
 constexpr int kXaR = 4;
 template <typename OutT>
 __global__ void __launch_bounds__(256, 1) slice_xattn_kernel(const float* __restrict__ Q, const float* __restrict__ KV,
-                                                             OutT* __restrict__ O, float* __restrict__ attn) {
+                                                             OutT* __restrict__ O, float* __restrict__ attn, DropSpec dr) {
   extern __shared__ float4 xa_smem[];
   float* sK = reinterpret_cast<float*>(xa_smem);       // [32][768]
   float* sV = sK + kNSlice * kHidden;                  // [32][768]
@@ -305,6 +306,8 @@ __global__ void __launch_bounds__(256, 1) slice_xattn_kernel(const float* __rest
       const float m = warp_max(sc[r]);
       const float e = expf(sc[r] - m);
       p[r] = e / warp_sum(e);
+      if (dr.on())      // train mode: p_attn = dropout(p_attn) (vit.py:31-32); the returned attention is the dropped one
+        p[r] *= drop_mask(dr.seed, dr.keep_thresh, dr.scale, static_cast<unsigned long long>(r0 + r) * kNSlice + lane);
       if (attn != nullptr) attn[(r0 + r) * kNSlice + lane] = p[r];
     }
     float4 acc[kXaR][kVecPerLane];
@@ -666,7 +669,7 @@ template int gather_rows<float>(const void*, int, long, long, int, int, float*, 
 template int gather_rows<__nv_bfloat16>(const void*, int, long, long, int, int, __nv_bfloat16*, cudaStream_t);
 
 template <typename OutT>
-int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn, int B, cudaStream_t stream) {
+int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn, int B, cudaStream_t stream, DropSpec dr) {
   if (B <= 0) return HS_OK;
   constexpr int smem = 2 * kNSlice * kHidden * 4;   // 196,608 B
   static unsigned char attr_set[kMaxDevices] = {0};
@@ -677,13 +680,60 @@ int slice_cross_attention(const float* Q, const float* KV, OutT* O, float* attn,
   }
   ProfScope prof(PROF_SLICE_XATTN, 4.0 * B * kNPatch * double(kNSlice) * kHidden,
                  double(B) * (kNPatch * kHidden * (4.0 + sizeof(OutT)) + kNSlice * 2.0 * kHidden * 4.0), stream);
-  slice_xattn_kernel<OutT><<<dim3(kNPatch / kXaRowsPerCta, B), 256, smem, stream>>>(Q, KV, O, attn);
+  slice_xattn_kernel<OutT><<<dim3(kNPatch / kXaRowsPerCta, B), 256, smem, stream>>>(Q, KV, O, attn, dr);
   count_launch();
   return launch_status();
 }
-template int slice_cross_attention<float>(const float*, const float*, float*, float*, int, cudaStream_t);
+template int slice_cross_attention<float>(const float*, const float*, float*, float*, int, cudaStream_t, DropSpec);
 template int slice_cross_attention<__nv_bfloat16>(const float*, const float*, __nv_bfloat16*, float*, int,
-                                                  cudaStream_t);
+                                                  cudaStream_t, DropSpec);
+
+// ---- train-mode dropout helpers (kernels.h DropSpec) ----------------------------------------------------------------
+DropSpec make_dropspec(float p, unsigned long long seed) {
+  DropSpec d;
+  if (p > 0.f) {
+    const double keep = 1.0 - static_cast<double>(p);
+    d.seed = seed;
+    d.keep_thresh = keep <= 0.0 ? 0u : static_cast<unsigned int>(keep * 4294967296.0 > 4294967295.0 ? 4294967295.0 : keep * 4294967296.0);
+    d.scale = keep <= 0.0 ? 1.0f : static_cast<float>(1.0 / keep);      // p = 1 drops everything (mask 0 either way)
+  }
+  return d;
+}
+namespace {
+template <int MODE>   // 0: z = resid + m z   1: out = m in   2: out = m
+__global__ void dropout_kernel(const float* __restrict__ in, const float* __restrict__ resid, float* __restrict__ out, long n,
+                               DropSpec dr) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float m = drop_mask(dr.seed, dr.keep_thresh, dr.scale, static_cast<unsigned long long>(i));
+    if (MODE == 0) out[i] = resid[i] + m * in[i];
+    else if (MODE == 1) out[i] = m * in[i];
+    else out[i] = m;
+  }
+}
+unsigned drop_grid(long n) {
+  const long blocks = (n + 255) / 256;
+  return static_cast<unsigned>(blocks < 148L * 16 ? (blocks > 0 ? blocks : 1) : 148L * 16);
+}
+}  // namespace
+int dropout_residual(float* z, const float* resid, long n, DropSpec dr, cudaStream_t st) {
+  if (n <= 0) return HS_OK;
+  dropout_kernel<0><<<drop_grid(n), 256, 0, st>>>(z, resid, z, n, dr);
+  count_launch();
+  return launch_status();
+}
+int dropout_scale(const float* in, float* out, long n, DropSpec dr, cudaStream_t st) {
+  if (n <= 0) return HS_OK;
+  dropout_kernel<1><<<drop_grid(n), 256, 0, st>>>(in, nullptr, out, n, dr);
+  count_launch();
+  return launch_status();
+}
+int dropout_mask(float* out, long n, DropSpec dr, cudaStream_t st) {
+  if (n <= 0) return HS_OK;
+  dropout_kernel<2><<<drop_grid(n), 256, 0, st>>>(nullptr, nullptr, out, n, dr);
+  count_launch();
+  return launch_status();
+}
 
 int score_and_scale(const float* Z, const float* ln_g, const float* ln_b, const float* w_s, const float* b_s,
                     const float* XP, float* X, float* scores, int B, cudaStream_t stream) {
@@ -709,18 +759,18 @@ template int packer_pool<float>(const float*, float*, int, cudaStream_t);
 template int packer_pool<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
 
 template <typename T>
-int packer_window_attention(const float* Q, const T* KV, T* O, int B, cudaStream_t stream) {
+int packer_window_attention(const float* Q, const T* KV, T* O, int B, cudaStream_t stream, DropSpec dr) {
   const long total = static_cast<long>(B) * 128;
   if (total <= 0) return HS_OK;
   ProfScope prof(PROF_PACKER_WATTN, 0.0,
                  double(B) * (128.0 * kHidden * (4.0 + sizeof(T)) + kNPatch * 2.0 * kHidden * sizeof(T)), stream);
-  packer_window_attn_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(Q, KV, O, total);
+  packer_window_attn_kernel<T><<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(Q, KV, O, total, dr);
   count_launch();
   return launch_status();
 }
-template int packer_window_attention<float>(const float*, const float*, float*, int, cudaStream_t);
+template int packer_window_attention<float>(const float*, const float*, float*, int, cudaStream_t, DropSpec);
 template int packer_window_attention<__nv_bfloat16>(const float*, const __nv_bfloat16*, __nv_bfloat16*, int,
-                                                    cudaStream_t);
+                                                    cudaStream_t, DropSpec);
 
 int l2_normalize_rows(const float* in, float* out, int rows, int dim, cudaStream_t stream) {
   if (rows <= 0) return HS_OK;

@@ -147,7 +147,9 @@ int grad_weight(const T* dYt, const T* Xt, int N, int K, int Mpad, float* dW, fl
 template <typename T>
 int vit_forward_train(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B, T* out_tokens,
                       T* out_patch, float* scores_out, void* tape_mem, size_t tape_bytes, void* workspace,
-                      size_t workspace_bytes, cudaStream_t st) {
+                      size_t workspace_bytes, const hsenet_dropout* drop, cudaStream_t st) {
+  const DropSpec drop_attn = drop ? make_dropspec(drop->p_attn, drop->seed_attn) : DropSpec();
+  const DropSpec drop_out = drop ? make_dropspec(drop->p_out, drop->seed_out) : DropSpec();
   const int L = w->num_layers;
   if (L > kMaxTapeLayers) return HS_ERR_ARG;
   VitTape<T> tp(tape_mem, B, w->stage, L);
@@ -183,11 +185,13 @@ int vit_forward_train(const hsenet_vit_weights* w, const float* images, const fl
       ep.bias = w->b_sq; ep.out_f32 = tp.Q; ep.ld_f32 = kHidden;
       HS_TRY(Prec<T>::gemm(tp.XPa, kHidden, w->w_sq, kHidden, Mp, kHidden, kHidden, ep, st));
     }
-    HS_TRY(slice_cross_attention<T>(tp.Q, tp.SKV, tp.O, nullptr, B, st));
+    HS_TRY(slice_cross_attention<T>(tp.Q, tp.SKV, tp.O, nullptr, B, st, drop_attn));
     {
-      GemmEpilogue ep;   // Z = Wq(x) + output_linear(o)
-      ep.bias = w->b_so; ep.resid = tp.Q; ep.ld_resid = kHidden; ep.out_f32 = tp.Z; ep.ld_f32 = kHidden;
+      GemmEpilogue ep;   // Z = Wq(x) + dropout_2(output_linear(o))   (vit.py:61-62)
+      ep.bias = w->b_so; ep.out_f32 = tp.Z; ep.ld_f32 = kHidden;
+      if (!drop_out.on()) { ep.resid = tp.Q; ep.ld_resid = kHidden; }
       HS_TRY(Prec<T>::gemm(tp.O, kHidden, w->w_so, kHidden, Mp, kHidden, kHidden, ep, st));
+      if (drop_out.on()) HS_TRY(dropout_residual(tp.Z, tp.Q, static_cast<long>(Mp) * kHidden, drop_out, st));
     }
     HS_TRY(score_and_scale(tp.Z, w->sn_g, w->sn_b, w->w_score, w->b_score, tp.XP, tp.X[0], tp.scores, B, st));
     if (scores_out != nullptr &&
@@ -232,7 +236,9 @@ int vit_forward_train(const hsenet_vit_weights* w, const float* images, const fl
 template <typename T>
 int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, const float* images, int B,
                  const T* d_tokens, const T* d_patch, void* tape_mem, size_t tape_bytes, const hsenet_vit_grads* g,
-                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                 void* workspace, size_t workspace_bytes, const hsenet_dropout* drop, cudaStream_t st) {
+  const DropSpec drop_attn = drop ? make_dropspec(drop->p_attn, drop->seed_attn) : DropSpec();
+  const DropSpec drop_out = drop ? make_dropspec(drop->p_out, drop->seed_out) : DropSpec();
   const int L = w->num_layers;
   if (L > kMaxTapeLayers) return HS_ERR_ARG;
   VitTape<T> tp(tape_mem, B, w->stage, L);
@@ -324,8 +330,13 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     if (g->sn_b) HS_TRY(colsum_finish(sp_b, ws.nblkp, kHidden, g->sn_b, st));
     if (g->w_score) HS_TRY(colsum_finish(sp_w, ws.nblkp, kHidden, g->w_score, st));
     if (g->b_score) HS_TRY(colsum_finish(sp_bs, ws.nblkp, 1, g->b_score, st));
-    // Z = Q + output_linear(O):  dZ -> output_linear (weight, bias, dO) and the residual branch into Q
-    HS_TRY((transpose_pad<float, T>(ws.dZ, kHidden, Mp, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_so ? ws.CS : nullptr, st)));
+    // Z = Q + dropout_2(output_linear(O)):  dZ -> output_linear (weight, bias, dO) and the residual branch into Q
+    const float* dlin = ws.dZ;
+    if (drop_out.on()) {             // gradient entering output_linear = mask o dZ (the residual branch keeps dZ)
+      HS_TRY(dropout_scale(ws.dZ, ws.dXN, static_cast<long>(Mp) * kHidden, drop_out, st));
+      dlin = ws.dXN;
+    }
+    HS_TRY((transpose_pad<float, T>(dlin, kHidden, Mp, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_so ? ws.CS : nullptr, st)));
     if (g->b_so) HS_TRY(colsum_finish(ws.CS, Mppad / 64, kHidden, g->b_so, st));
     HS_TRY((transpose_pad<T, T>(tp.O, kHidden, Mp, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
     HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mppad, g->w_so, ws.DWP, st));
@@ -336,7 +347,7 @@ int vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, co
     }
     // attention core: dQ = dZ (residual) + dQ_attention;  dK | dV of the 32 slice keys
     float* dQ = ws.dZ;               // in place: the kernel adds its contribution to dZ
-    HS_TRY(slice_xattn_bwd<T>(tp.Q, tp.SKV, ws.dATT, dQ, 1, ws.Pm, ws.dSm, ws.dSKV, B, st));
+    HS_TRY(slice_xattn_bwd<T>(tp.Q, tp.SKV, ws.dATT, dQ, 1, ws.Pm, ws.dSm, ws.dSKV, B, st, drop_attn));
     // Wk | Wv of the slice features: dW = dSKV^T S16, db = colsum(dSKV)
     if (g->w_skv != nullptr || g->b_skv != nullptr) {
       const int R = B * kNSlice, Rpad = padded_rows(R);
@@ -451,7 +462,9 @@ struct PackerTrainWs {
 
 template <typename T>
 int packer_forward_train(const hsenet_packer_weights* w, const T* hr, int B, T* out, void* tape_mem, size_t tape_bytes,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                         void* workspace, size_t workspace_bytes, const hsenet_dropout* drop, cudaStream_t st) {
+  const DropSpec drop_attn = drop ? make_dropspec(drop->p_attn, drop->seed_attn) : DropSpec();
+  const DropSpec drop_out = drop ? make_dropspec(drop->p_out, drop->seed_out) : DropSpec();
   const int D = w->out_dim;
   if (D <= 0 || D % 256 != 0) return HS_ERR_SHAPE;
   PackerTape<T> tp(tape_mem, B, D);
@@ -469,11 +482,13 @@ int packer_forward_train(const hsenet_packer_weights* w, const T* hr, int B, T* 
     ep.bias = w->b_q; ep.out_f32 = tp.Q; ep.ld_f32 = kHidden;
     HS_TRY(Prec<T>::gemm(tp.LR, kHidden, w->w_q, kHidden, Mw, kHidden, kHidden, ep, st));
   }
-  HS_TRY(packer_window_attention<T>(tp.Q, tp.KV, tp.O, B, st));
+  HS_TRY(packer_window_attention<T>(tp.Q, tp.KV, tp.O, B, st, drop_attn));
   {
-    GemmEpilogue ep;
-    ep.bias = w->b_o; ep.resid = tp.Q; ep.ld_resid = kHidden; ep.out_f32 = tp.Z; ep.ld_f32 = kHidden;
+    GemmEpilogue ep;   // Z = Wq(LR) + dropout_2(output_linear(o))   (spatial_pooling_projector.py:77-78)
+    ep.bias = w->b_o; ep.out_f32 = tp.Z; ep.ld_f32 = kHidden;
+    if (!drop_out.on()) { ep.resid = tp.Q; ep.ld_resid = kHidden; }
     HS_TRY(Prec<T>::gemm(tp.O, kHidden, w->w_o, kHidden, Mw, kHidden, kHidden, ep, st));
+    if (drop_out.on()) HS_TRY(dropout_residual(tp.Z, tp.Q, static_cast<long>(Mw) * kHidden, drop_out, st));
   }
   HS_TRY(layernorm_rows<T>(tp.Z, kHidden, w->ln_g, w->ln_b, Mw, tp.A, kHidden, nullptr, 128, st));
   {
@@ -493,7 +508,9 @@ int packer_forward_train(const hsenet_packer_weights* w, const T* hr, int B, T* 
 template <typename T>
 int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_t* wt, const T* hr, int B, const T* d_out,
                     void* tape_mem, size_t tape_bytes, const hsenet_packer_grads* g, float* d_hr, void* workspace,
-                    size_t workspace_bytes, cudaStream_t st) {
+                    size_t workspace_bytes, const hsenet_dropout* drop, cudaStream_t st) {
+  const DropSpec drop_attn = drop ? make_dropspec(drop->p_attn, drop->seed_attn) : DropSpec();
+  const DropSpec drop_out = drop ? make_dropspec(drop->p_out, drop->seed_out) : DropSpec();
   const int D = w->out_dim;
   if (D <= 0 || D % 256 != 0) return HS_ERR_SHAPE;
   PackerTape<T> tp(tape_mem, B, D);
@@ -528,8 +545,13 @@ int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_
                        g->ln_b ? lnp_b : nullptr, st));
   if (g->ln_g) HS_TRY(colsum_finish(lnp_g, ws.nblk, kHidden, g->ln_g, st));
   if (g->ln_b) HS_TRY(colsum_finish(lnp_b, ws.nblk, kHidden, g->ln_b, st));
-  // Z = Q + output_linear(O): ws.dQ holds dZ = the residual part of dQ
-  HS_TRY((transpose_pad<float, T>(ws.dQ, kHidden, Mw, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_o ? ws.CS : nullptr, st)));
+  // Z = Q + dropout_2(output_linear(O)): ws.dQ holds dZ = the residual part of dQ; output_linear sees mask o dZ
+  const float* dlin = ws.dQ;
+  if (drop_out.on()) {
+    HS_TRY(dropout_scale(ws.dQ, ws.dF, static_cast<long>(Mw) * kHidden, drop_out, st));
+    dlin = ws.dF;
+  }
+  HS_TRY((transpose_pad<float, T>(dlin, kHidden, Mw, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_o ? ws.CS : nullptr, st)));
   if (g->b_o) HS_TRY(colsum_finish(ws.CS, Mwpad / 64, kHidden, g->b_o, st));
   HS_TRY((transpose_pad<T, T>(tp.O, kHidden, Mw, kHidden, ws.TB, nullptr, 0, 0, nullptr, st)));
   HS_TRY(grad_weight<T>(ws.TA, ws.TB, kHidden, kHidden, Mwpad, g->w_o, ws.DWP, st));
@@ -539,7 +561,7 @@ int packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_
     HS_TRY(Prec<T>::gemm(ws.dYb, kHidden, wt->w_o_t, kHidden, Mw, kHidden, kHidden, ep, st));
   }
   // per-window attention: dQ_attn (into dF), dKV
-  HS_TRY(window_attn_bwd<T>(ws.dO, tp.Q, tp.KV, ws.dF, ws.dKV, B, st));
+  HS_TRY(window_attn_bwd<T>(ws.dO, tp.Q, tp.KV, ws.dF, ws.dKV, B, st, drop_attn));
   HS_TRY(add_rows(ws.dQ, ws.dF, static_cast<long>(Mw) * kHidden, st));       // dQ = dZ + dQ_attn
   // Wq(LR)
   HS_TRY((transpose_pad<float, T>(ws.dQ, kHidden, Mw, kHidden, ws.TA, ws.dYb, kHidden, 0, g->b_q ? ws.CS : nullptr, st)));
@@ -627,26 +649,29 @@ size_t hsenet_vit_train_workspace_bytes(int B, int precision, int stage) {
 
 int hsenet_vit_forward_train(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B,
                              int precision, void* out_tokens, void* out_patch, float* scores_f32, void* tape,
-                             size_t tape_bytes, void* workspace, size_t workspace_bytes, hsenet_stream_t stream) {
+                             size_t tape_bytes, void* workspace, size_t workspace_bytes, const hsenet_dropout* dropout,
+                             hsenet_stream_t stream) {
   if (w == nullptr || images == nullptr || tape == nullptr || workspace == nullptr || w->blocks_host == nullptr)
+    return HSENET_ERR_ARG;
+  if (dropout != nullptr && !(dropout->p_attn >= 0.f && dropout->p_attn < 1.f && dropout->p_out >= 0.f && dropout->p_out < 1.f))
     return HSENET_ERR_ARG;
   if (B <= 0 || w->num_layers < 0 || (w->stage != 1 && w->stage != 2)) return HSENET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == HSENET_PREC_BF16)
     return vit_forward_train<__nv_bfloat16>(w, images, images_2d, B, static_cast<__nv_bfloat16*>(out_tokens),
                                             static_cast<__nv_bfloat16*>(out_patch), scores_f32, tape, tape_bytes,
-                                            workspace, workspace_bytes, st);
+                                            workspace, workspace_bytes, dropout, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return vit_forward_train<float>(w, images, images_2d, B, static_cast<float*>(out_tokens),
                                     static_cast<float*>(out_patch), scores_f32, tape, tape_bytes, workspace,
-                                    workspace_bytes, st);
+                                    workspace_bytes, dropout, st);
   return HSENET_ERR_ARG;
 }
 
 int hsenet_vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, const float* images, int B,
                         int precision, const void* d_tokens, const void* d_patch, const void* tape, size_t tape_bytes,
                         const hsenet_vit_grads* grads, void* workspace, size_t workspace_bytes,
-                        hsenet_stream_t stream) {
+                        const hsenet_dropout* dropout, hsenet_stream_t stream) {
   if (w == nullptr || wt == nullptr || images == nullptr || tape == nullptr || grads == nullptr || workspace == nullptr ||
       w->blocks_host == nullptr || wt->blocks_host == nullptr || grads->blocks_host == nullptr)
     return HSENET_ERR_ARG;
@@ -656,10 +681,10 @@ int hsenet_vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t*
   if (precision == HSENET_PREC_BF16)
     return vit_backward<__nv_bfloat16>(w, wt, images, B, static_cast<const __nv_bfloat16*>(d_tokens),
                                        static_cast<const __nv_bfloat16*>(d_patch), tp, tape_bytes, grads, workspace,
-                                       workspace_bytes, st);
+                                       workspace_bytes, dropout, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return vit_backward<float>(w, wt, images, B, static_cast<const float*>(d_tokens), static_cast<const float*>(d_patch),
-                               tp, tape_bytes, grads, workspace, workspace_bytes, st);
+                               tp, tape_bytes, grads, workspace, workspace_bytes, dropout, st);
   return HSENET_ERR_ARG;
 }
 
@@ -679,24 +704,26 @@ size_t hsenet_packer_train_workspace_bytes(int B, int precision, int out_dim) {
 
 int hsenet_packer_forward_train(const hsenet_packer_weights* w, const void* hr, int B, int precision, void* out,
                                 void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
-                                hsenet_stream_t stream) {
+                                const hsenet_dropout* dropout, hsenet_stream_t stream) {
   if (w == nullptr || hr == nullptr || out == nullptr || tape == nullptr || workspace == nullptr || B <= 0)
+    return HSENET_ERR_ARG;
+  if (dropout != nullptr && !(dropout->p_attn >= 0.f && dropout->p_attn < 1.f && dropout->p_out >= 0.f && dropout->p_out < 1.f))
     return HSENET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == HSENET_PREC_BF16)
     return packer_forward_train<__nv_bfloat16>(w, static_cast<const __nv_bfloat16*>(hr), B,
                                                static_cast<__nv_bfloat16*>(out), tape, tape_bytes, workspace,
-                                               workspace_bytes, st);
+                                               workspace_bytes, dropout, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return packer_forward_train<float>(w, static_cast<const float*>(hr), B, static_cast<float*>(out), tape, tape_bytes,
-                                       workspace, workspace_bytes, st);
+                                       workspace, workspace_bytes, dropout, st);
   return HSENET_ERR_ARG;
 }
 
 int hsenet_packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_t* wt, const void* hr, int B,
                            int precision, const void* d_out, const void* tape, size_t tape_bytes,
                            const hsenet_packer_grads* grads, float* d_hr, void* workspace, size_t workspace_bytes,
-                           hsenet_stream_t stream) {
+                           const hsenet_dropout* dropout, hsenet_stream_t stream) {
   if (w == nullptr || wt == nullptr || hr == nullptr || d_out == nullptr || tape == nullptr || grads == nullptr ||
       workspace == nullptr || B <= 0)
     return HSENET_ERR_ARG;
@@ -705,11 +732,18 @@ int hsenet_packer_backward(const hsenet_packer_weights* w, const hsenet_packer_w
   if (precision == HSENET_PREC_BF16)
     return packer_backward<__nv_bfloat16>(w, wt, static_cast<const __nv_bfloat16*>(hr), B,
                                           static_cast<const __nv_bfloat16*>(d_out), tp, tape_bytes, grads, d_hr,
-                                          workspace, workspace_bytes, st);
+                                          workspace, workspace_bytes, dropout, st);
   if (precision == HSENET_PREC_FP32_VERIFY)
     return packer_backward<float>(w, wt, static_cast<const float*>(hr), B, static_cast<const float*>(d_out), tp,
-                                  tape_bytes, grads, d_hr, workspace, workspace_bytes, st);
+                                  tape_bytes, grads, d_hr, workspace, workspace_bytes, dropout, st);
   return HSENET_ERR_ARG;
+}
+
+int hsenet_dropout_mask(float p, unsigned long long seed, long long n, float* out, hsenet_stream_t stream) {
+  if (out == nullptr || n < 0 || !(p >= 0.f && p < 1.f)) return HSENET_ERR_ARG;
+  DropSpec d = make_dropspec(p, seed);
+  if (!d.on()) { d.keep_thresh = 0xffffffffu; d.scale = 1.0f; }      // p = 0: all ones
+  return dropout_mask(out, static_cast<long>(n), d, static_cast<cudaStream_t>(stream));
 }
 
 int hsenet_self_attention_ws(const void* qkv, void* out, float* lse, float* scratch, int B, int S, int precision,

@@ -27,9 +27,11 @@ def pack_features(feats, mm_projector, mm_projector2, out_dtype=None):
         second = mm_projector2 if mm_projector2 is not None else mm_projector   # fallback of lamed_arch.py:128-131
         n1, n2 = mm_projector.proj_out_num, second.proj_out_num
         dt = out_dtype or mm_projector.output_dtype or rt.act_dtype()
-        if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad or any(
-                p.requires_grad for m in (mm_projector, second) for p in m.parameters())):
-            # training: the packers run through their autograd Functions; the concatenation is the reference's
+        drops = any(getattr(m, "_dropout_active", lambda: False)() for m in (mm_projector, second))
+        if drops or (torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad or any(
+                p.requires_grad for m in (mm_projector, second) for p in m.parameters()))):
+            # training (or train()-mode dropout): the packers run through their autograd Functions; the concatenation is
+            # the reference's
             return torch.cat([mm_projector(f1), second(f2)], dim=1).to(dt)
         out = torch.empty(f1.shape[0], n1 + n2, mm_projector.out_dim, dtype=dt, device=f1.device)
         mm_projector.forward_into(f1, out, 0)
@@ -86,7 +88,9 @@ def splice_visual_tokens(tower, mm_projector, mm_projector2, inputs_embeds, imag
     needs_grad = torch.is_grad_enabled() and (
         inputs_embeds.requires_grad or any(p.requires_grad for m in (tower, mm_projector, second)
                                            for p in m.parameters()))
-    if needs_grad:
+    # packers in train() mode apply dropout, which only their module forward (not forward_into) implements
+    drops = any(getattr(m, "_dropout_active", lambda: False)() for m in (mm_projector, second))
+    if needs_grad or drops:
         vis = pack_features(feats, mm_projector, mm_projector2)
         out = inputs_embeds.clone(memory_format=torch.contiguous_format)
         out[:, 1:1 + n1 + n2] = vis.to(out.dtype)

@@ -64,8 +64,14 @@ class VisualPacker_3d_phi_v3(nn.Module):
         self._cache = rt.WeightCache()
         self._train_cache = rt.WeightCache()
 
+    def _dropout_active(self) -> bool:
+        """True in ``.train()`` mode with p > 0 on resolution_attention's nn.Dropout members
+        (spatial_pooling_projector.py:58-59): the forward then runs the training kernels, which apply dropout."""
+        a = self.resolution_attention
+        return bool(self.training and (a.dropout.p > 0 or a.dropout_2.p > 0))
+
     def disable_dropout(self):
-        """Set p = 0 on the two Dropout members of resolution_attention (the kernels do not apply dropout)."""
+        """Set p = 0 on the two Dropout members of resolution_attention (train without dropout)."""
         for m in self.modules():
             if isinstance(m, nn.Dropout):
                 m.p = 0.0
@@ -94,16 +100,8 @@ class VisualPacker_3d_phi_v3(nn.Module):
         pl["struct_t"] = wt
         return pl
 
-    def _check_dropout(self):
-        if self.training and self.resolution_attention.dropout.p > 0:
-            raise NotImplementedError(
-                "VisualPacker_3d_phi_v3 in .train() mode applies Dropout(p=0.1) inside resolution_attention "
-                "(spatial_pooling_projector.py:58-59); the hsenet_b200 kernels do not apply dropout -- call .eval() "
-                "or .disable_dropout() (p = 0)")
-
     def _forward_train(self, visual_inputs):
         rt.require_cuda(visual_inputs, "visual_inputs")
-        self._check_dropout()
         if visual_inputs.dim() != 3 or visual_inputs.shape[1] != N_PATCH or visual_inputs.shape[2] != HIDDEN:
             raise ValueError(f"expected visual_inputs [B,2048,768], got {tuple(visual_inputs.shape)}")
         out = tr.PackerTrainFn.apply(self, visual_inputs, *self.parameters())
@@ -145,7 +143,9 @@ class VisualPacker_3d_phi_v3(nn.Module):
         if tr.needs_grad(self, visual_inputs):
             raise RuntimeError("forward_into writes through raw pointers and is invisible to autograd; call the module "
                                "(forward) when gradients are required")
-        self._check_dropout()
+        if self._dropout_active():
+            raise RuntimeError("forward_into is the inference path and applies no dropout; this packer is in train() "
+                               "mode with p > 0 -- call the module (forward), .eval() or .disable_dropout()")
         if visual_inputs.dim() != 3 or visual_inputs.shape[1] != N_PATCH or visual_inputs.shape[2] != HIDDEN:
             raise ValueError(f"expected visual_inputs [B,2048,768], got {tuple(visual_inputs.shape)}")
         if visual_inputs.stride(2) != 1:
@@ -179,7 +179,7 @@ class VisualPacker_3d_phi_v3(nn.Module):
         return out
 
     def forward(self, visual_inputs):
-        if tr.needs_grad(self, visual_inputs):
+        if tr.needs_grad(self, visual_inputs) or self._dropout_active():
             return self._forward_train(visual_inputs)
         B = visual_inputs.shape[0]
         dt = self.output_dtype or rt.act_dtype()

@@ -8,9 +8,11 @@ per parameter.  The Functions take the module's parameters as explicit inputs, i
 routes the returned gradients to them (DDP hooks, gradient accumulation and optimizers work unchanged).
 
 Train-mode dropout of the two small attentions (``regular_attention`` / ``resolution_attention_v3``, p = 0.1 on the
-attention probabilities and on the output projection): not applied by these kernels.  The façades therefore only take
-the training path when the module is in ``eval()`` mode or its dropout probability is 0 (``module.disable_dropout()``);
-otherwise they raise instead of silently training a different model.
+attention probabilities and on the output projection in front of the residual add): applied inside the kernels from a
+counter-based keep mask (``hsenet_dropout`` in include/hsenet_b200.h).  Two 63-bit seeds per call are drawn from torch's
+CPU generator (``torch.manual_seed`` makes a run repeatable); the backward regenerates the masks from the same seeds.
+The random stream differs from torch's own dropout kernels, so a run matches the reference in distribution, not bit for
+bit; ``dropout_mask()`` returns the exact mask a seed stands for (the parity tests feed it to the oracle).
 """
 from __future__ import annotations
 
@@ -43,6 +45,32 @@ def transpose_weight(w: torch.Tensor, prec: str) -> torch.Tensor:
     return out
 
 
+def draw_dropout(attn_module, training: bool):
+    """``_lib.Dropout`` for one forward/backward pair of a small-attention module (members ``dropout`` on the
+    probabilities and ``dropout_2`` on the output projection), or None when both are inactive (eval / p == 0)."""
+    pa, po = float(attn_module.dropout.p), float(attn_module.dropout_2.p)
+    if not training or (pa <= 0.0 and po <= 0.0):
+        return None
+    if pa >= 1.0 or po >= 1.0:
+        raise ValueError("hsenet_b200: dropout p must be < 1")
+    seeds = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)      # CPU generator: follows torch.manual_seed
+    return _lib.Dropout(max(pa, 0.0), max(po, 0.0), int(seeds[0]), int(seeds[1]))
+
+
+def dropout_mask(p: float, seed: int, shape, device) -> torch.Tensor:
+    """The keep mask (0 or 1/(1-p), fp32) the kernels apply for (p, seed) over a row-major tensor of ``shape``."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = _lib.load().hsenet_dropout_mask(C.c_float(p), C.c_ulonglong(seed), out.numel(), out.data_ptr(),
+                                             rt.stream_ptr(device))
+    _lib.check(rc, "dropout_mask")
+    return out
+
+
+def _drop_ref(d):
+    return C.byref(d) if d is not None else None
+
+
 def _grad_like(p: torch.Tensor, want: bool):
     return torch.empty(p.shape, dtype=torch.float32, device=p.device) if want else None
 
@@ -72,10 +100,14 @@ class VitTrainFn(torch.autograd.Function):
             tokens = torch.empty(B, 2049, 768, dtype=act, device=dev)
             patch = torch.empty(B, 2048, 768, dtype=act, device=dev)
             scores = torch.empty(B, 2048, dtype=torch.float32, device=dev) if stage == 2 else None
+            drop = draw_dropout(module.slice_guided_attention, module.training) if stage == 2 else None
             rc = lib.hsenet_vit_forward_train(C.byref(payload["struct"]), xin.data_ptr(), rt.ptr(s2d), B, pc,
                                               tokens.data_ptr(), patch.data_ptr(), rt.ptr(scores), tape.data_ptr(),
-                                              tape.numel(), ws.data_ptr(), ws.numel(), rt.stream_ptr(dev))
+                                              tape.numel(), ws.data_ptr(), ws.numel(), _drop_ref(drop),
+                                              rt.stream_ptr(dev))
         _lib.check(rc, f"vit_forward_train(stage={stage})")
+        ctx.drop = drop
+        module.last_dropout = drop
         ctx.module, ctx.prec, ctx.payload, ctx.tape, ctx.xin, ctx.B = module, prec, payload, tape, xin, B
         ctx.param_needs = [p.requires_grad for p in params]
         module.last_scores = scores
@@ -140,7 +172,7 @@ class VitTrainFn(torch.autograd.Function):
             ws = rt.workspace(dev, lib.hsenet_vit_train_workspace_bytes(B, pc, stage), "vit_train")
             rc = lib.hsenet_vit_backward(C.byref(payload["struct"]), C.byref(payload["struct_t"]), ctx.xin.data_ptr(), B,
                                          pc, rt.ptr(dt), rt.ptr(dp), ctx.tape.data_ptr(), ctx.tape.numel(), C.byref(vg),
-                                         ws.data_ptr(), ws.numel(), rt.stream_ptr(dev))
+                                         ws.data_ptr(), ws.numel(), _drop_ref(ctx.drop), rt.stream_ptr(dev))
         _lib.check(rc, f"vit_backward(stage={stage})")
         if stage == 2:
             a = module.slice_guided_attention
@@ -183,10 +215,13 @@ class PackerTrainFn(torch.autograd.Function):
             tape = torch.empty(lib.hsenet_packer_tape_bytes(B, pc, D), dtype=torch.uint8, device=dev)
             ws = rt.workspace(dev, lib.hsenet_packer_train_workspace_bytes(B, pc, D), "packer_train")
             out = torch.empty(B, 128, D, dtype=act, device=dev)
+            drop = draw_dropout(module.resolution_attention, module.training)
             rc = lib.hsenet_packer_forward_train(C.byref(payload["struct"]), hr.data_ptr(), B, pc, out.data_ptr(),
                                                  tape.data_ptr(), tape.numel(), ws.data_ptr(), ws.numel(),
-                                                 rt.stream_ptr(dev))
+                                                 _drop_ref(drop), rt.stream_ptr(dev))
         _lib.check(rc, "packer_forward_train")
+        ctx.drop = drop
+        module.last_dropout = drop
         ctx.module, ctx.prec, ctx.payload, ctx.tape, ctx.hr, ctx.B = module, prec, payload, tape, hr, B
         ctx.param_needs = [p.requires_grad for p in params]
         ctx.hr_needs = hr_in.requires_grad
@@ -226,7 +261,8 @@ class PackerTrainFn(torch.autograd.Function):
             ws = rt.workspace(dev, lib.hsenet_packer_train_workspace_bytes(B, pc, D), "packer_train")
             rc = lib.hsenet_packer_backward(C.byref(payload["struct"]), C.byref(payload["struct_t"]), ctx.hr.data_ptr(), B,
                                             pc, do.data_ptr(), ctx.tape.data_ptr(), ctx.tape.numel(), C.byref(pg),
-                                            rt.ptr(d_hr), ws.data_ptr(), ws.numel(), rt.stream_ptr(dev))
+                                            rt.ptr(d_hr), ws.data_ptr(), ws.numel(), _drop_ref(ctx.drop),
+                                            rt.stream_ptr(dev))
         _lib.check(rc, "packer_backward")
         for (wp, src, lo) in ((a.Wk.weight, wkv, 0), (a.Wv.weight, wkv, 768), (a.Wk.bias, bkv, 0), (a.Wv.bias, bkv, 768)):
             if src is not None and grads[id(wp)] is not None:

@@ -241,9 +241,15 @@ class _ViTBase(nn.Module):
         pl["blocks_t"] = bt
         return pl
 
+    def _dropout_active(self) -> bool:
+        """True when a forward has to apply dropout: ViT_stage2 in ``.train()`` mode (slice_guided_attention carries
+        two nn.Dropout(p=0.1), vit.py:46-47).  Such a forward runs the training kernels, which apply it."""
+        a = getattr(self, "slice_guided_attention", None)
+        return bool(self.training and a is not None and (a.dropout.p > 0 or a.dropout_2.p > 0))
+
     def disable_dropout(self):
-        """Set p = 0 on the Dropout members of the slice-guided attention (the training kernels do not apply dropout;
-        see hsenet_b200/training.py).  ViT_stage1 has none."""
+        """Set p = 0 on the Dropout members of the slice-guided attention (ViT_stage1 has none): the module then
+        trains without dropout and its no-grad forwards stay on the graph-captured inference path in train() mode."""
         for m in self.modules():
             if isinstance(m, nn.Dropout):
                 m.p = 0.0
@@ -257,7 +263,7 @@ class _ViTBase(nn.Module):
         self._graphs.clear()
 
     def _run(self, x, image_2d):
-        if tr.needs_grad(self):
+        if tr.needs_grad(self) or self._dropout_active():
             return self._run_train(x, image_2d)
         return self._finish(self._launch(x, image_2d))
 
@@ -439,14 +445,7 @@ class ViT_stage2(_ViTBase):
             raise ValueError("hsenet_b200: classification=True (cls token) is what every reference caller uses")
         self._finish_init()
 
-    def _check_mode(self):
-        if self.training and self.slice_guided_attention.dropout.p > 0:
-            raise NotImplementedError(
-                "ViT_stage2 in .train() mode applies Dropout(p=0.1) inside slice_guided_attention (vit.py:46-47); "
-                "the hsenet_b200 kernels do not apply dropout -- call .eval() or .disable_dropout() (p = 0)")
-
     def forward(self, x, image_2d, k=None, visual_encoder_2D=None, text_features=None, image_path=None):
-        self._check_mode()
         return self._run(x, image_2d)
 
 
@@ -477,7 +476,8 @@ class ViT3DTower_dual_encoders(nn.Module):
         if self.select_feature not in ("patch", "cls_patch"):
             raise ValueError(f"Unexpected select feature: {self.select_feature}")
         feats = []
-        if t == "dual_vits" and self.concurrent_towers and images.is_cuda and not tr.needs_grad(self):
+        if t == "dual_vits" and self.concurrent_towers and images.is_cuda and not tr.needs_grad(self) and \
+                not self.vision_tower_stage2._dropout_active():
             return self._forward_concurrent(images, images_2d)     # frozen towers (VLM stage): graph replays on two streams
         # the reference always runs both encoders (vit.py:928-929); skipping the unused one changes no result
         if t in ("dual_vits", "3d_vit"):
@@ -504,7 +504,6 @@ class ViT3DTower_dual_encoders(nn.Module):
         dev = images.device
         cur = torch.cuda.current_stream(dev)
         side = rt.side_stream(dev)
-        t2._check_mode()
         # One implicit-im2col GEMM writes the patch embeddings of BOTH encoders (they read the same volume, vit.py:928-929):
         # N = 1536 over the stacked fp32 projections, results straight into the two workspaces (bf16 precision only).
         dual = self.shared_patch_embedding and rt.get_precision() == "bf16" and \

@@ -286,6 +286,22 @@ typedef struct hsenet_packer_grads {
   float *w_q, *b_q, *w_kv, *b_kv, *w_o, *b_o, *ln_g, *ln_b, *w_p0, *b_p0, *w_p2, *b_p2;
 } hsenet_packer_grads;
 
+/* Train-mode dropout of the two small attentions: regular_attention (vit.py:25-33, 46-47, 60-62) and resolution_attention_v3
+ * (spatial_pooling_projector.py:8-16, 58-59, 76-78) apply nn.Dropout(p = 0.1) to the attention probabilities and to the
+ * output_linear result in front of the residual add.  The kernels use a counter-based keep mask: element i of the tensor is
+ * kept when the top 32 bits of splitmix64(seed + (i + 1) * 0x9E3779B97F4A7C15) are < (1 - p) * 2^32, and scaled by
+ * 1 / (1 - p); i runs over the row-major [rows, 32] / [windows, 16] probabilities (seed_attn) and the [rows, 768]
+ * projection (seed_out).  The backward call must receive the forward's struct (the mask is regenerated, not stored).
+ * NULL or p_* = 0: no dropout (eval).  Different random stream from torch's: statistically, not bitwise, the reference's. */
+typedef struct hsenet_dropout {
+  float p_attn;                  /* nn.Dropout on the attention probabilities, 0 <= p < 1 (0: off) */
+  float p_out;                   /* nn.Dropout (dropout_2) on the output projection                */
+  unsigned long long seed_attn;
+  unsigned long long seed_out;
+} hsenet_dropout;
+/* out[i] = keep-mask value (0 or 1 / (1 - p)) of element i, fp32: what the kernels multiply by (tests, debugging). */
+int hsenet_dropout_mask(float p, unsigned long long seed, long long n, float* out, hsenet_stream_t stream);
+
 /* out[cols,rows] = in[rows,cols]^T, fp32 in, activation dtype out (HSENET_DTYPE_BF16 / _F32). */
 int hsenet_transpose_weight(const float* in, int rows, int cols, void* out, int out_dtype, hsenet_stream_t stream);
 
@@ -295,26 +311,27 @@ size_t hsenet_vit_train_workspace_bytes(int B, int precision, int stage);
  * exact erf form applied to the bf16-rounded pre-activation (the pre-activation is what the tape keeps). */
 int hsenet_vit_forward_train(const hsenet_vit_weights* w, const float* images, const float* images_2d, int B,
                              int precision, void* out_tokens, void* out_patch, float* scores_f32, void* tape,
-                             size_t tape_bytes, void* workspace, size_t workspace_bytes, hsenet_stream_t stream);
+                             size_t tape_bytes, void* workspace, size_t workspace_bytes, const hsenet_dropout* dropout,
+                             hsenet_stream_t stream);
 /* d_tokens [B,2049,768] / d_patch [B,2048,768] in the activation dtype: gradients of the two outputs (either may be
  * NULL).  images: the forward's input (the patch matrix is re-derived from it, not taped). */
 int hsenet_vit_backward(const hsenet_vit_weights* w, const hsenet_vit_weights_t* wt, const float* images, int B,
                         int precision, const void* d_tokens, const void* d_patch, const void* tape, size_t tape_bytes,
                         const hsenet_vit_grads* grads, void* workspace, size_t workspace_bytes,
-                        hsenet_stream_t stream);
+                        const hsenet_dropout* dropout, hsenet_stream_t stream);
 
 size_t hsenet_packer_tape_bytes(int B, int precision, int out_dim);
 size_t hsenet_packer_train_workspace_bytes(int B, int precision, int out_dim);
 /* out: [B,128,out_dim] contiguous in the activation dtype. */
 int hsenet_packer_forward_train(const hsenet_packer_weights* w, const void* hr, int B, int precision, void* out,
                                 void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
-                                hsenet_stream_t stream);
+                                const hsenet_dropout* dropout, hsenet_stream_t stream);
 /* d_out [B,128,out_dim] activation dtype; hr: the forward's input.  d_hr (optional): fp32 [B,2048,768] gradient of the
  * tower features (needs wt->w_kv_t). */
 int hsenet_packer_backward(const hsenet_packer_weights* w, const hsenet_packer_weights_t* wt, const void* hr, int B,
                            int precision, const void* d_out, const void* tape, size_t tape_bytes,
                            const hsenet_packer_grads* grads, float* d_hr, void* workspace, size_t workspace_bytes,
-                           hsenet_stream_t stream);
+                           const hsenet_dropout* dropout, hsenet_stream_t stream);
 
 /* ---- online 2D-slice branch -------------------------------------------------------------
  * Replaces the offline JPG -> BiomedCLIP -> npy pipeline (Data/data_processing/CT-RATE/CT-RATE_2D_to_npy_file.py:75-98) and

@@ -138,40 +138,47 @@ def vit_stage1(sd, x: torch.Tensor):
     return _ln(h, sd, "norm"), hidden
 
 
-def single_head_attention(q, k, v):
+def single_head_attention(q, k, v, drop_mask=None):
     """``attention`` helper, vit.py:25-33 == spatial_pooling_projector.py:8-16: one head, d_k = full
-    embedding width (768), no mask, dropout inactive in eval."""
+    embedding width (768), no mask.  ``drop_mask`` restates ``p_attn = dropout(p_attn)`` (vit.py:31-32) of train mode
+    with an explicit keep mask (0 or 1/(1-p), shape of the probabilities) instead of torch's RNG; None = eval."""
     scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.size(-1))
     p = F.softmax(scores, dim=-1)
+    if drop_mask is not None:
+        p = p * drop_mask
     return torch.matmul(p, v), p
 
 
-def regular_attention(sd, query, key, value, prefix="slice_guided_attention"):
-    """regular_attention.forward, vit.py:50-64.  NB the residual is the *projected* query (:62)."""
+def regular_attention(sd, query, key, value, prefix="slice_guided_attention", drop=None):
+    """regular_attention.forward, vit.py:50-64.  NB the residual is the *projected* query (:62).  ``drop`` = (mask on the
+    probabilities [B,2048,32], mask on the output projection [B,2048,768]) restates the two nn.Dropout members of train
+    mode (:60 ``dropout``, :62 ``dropout_2``) with explicit keep masks."""
     ql = _lin(query, sd, prefix + ".Wq")
     kl = _lin(key, sd, prefix + ".Wk")
     vl = _lin(value, sd, prefix + ".Wv")
-    x, attn = single_head_attention(ql, kl, vl)
+    x, attn = single_head_attention(ql, kl, vl, None if drop is None else drop[0])
     x = _lin(x, sd, prefix + ".output_linear")
+    if drop is not None:
+        x = x * drop[1]
     x = _ln(ql + x, sd, prefix + ".norm")
     return x, attn
 
 
-def patch_scores(sd, xp: torch.Tensor, image_2d: torch.Tensor):
+def patch_scores(sd, xp: torch.Tensor, image_2d: torch.Tensor, drop=None):
     """vit.py:332-339: slice features [B,32,768] guide a cross attention from the 2048 patch tokens;
     patch_score_proj (768->1) then Sigmoid -> scores [B,2048]."""
     b = xp.shape[0]
     sem = image_2d.float().reshape(b, N_SLICE, -1)
-    ps, att = regular_attention(sd, xp, sem, sem)
+    ps, att = regular_attention(sd, xp, sem, sem, drop=drop)
     s = _lin(ps, sd, "patch_score_proj").reshape(b, xp.shape[1])
     return torch.sigmoid(s), att
 
 
-def vit_stage2(sd, x: torch.Tensor, image_2d: torch.Tensor):
+def vit_stage2(sd, x: torch.Tensor, image_2d: torch.Tensor, drop=None):
     """ViT_stage2.forward, vit.py:315-357: patch embed -> scores (332-339) -> x*score (345) -> prepend cls
     (347-349) -> blocks (351-354) -> LayerNorm (355)."""
     xp = patch_embedding(sd, x)
-    scores, _ = patch_scores(sd, xp, image_2d)
+    scores, _ = patch_scores(sd, xp, image_2d, drop=drop)
     h = xp * scores.unsqueeze(-1)
     if "cls_token" in sd:
         h = torch.cat((sd["cls_token"].expand(h.shape[0], -1, -1), h), dim=1)
@@ -212,7 +219,7 @@ def packer_pool(feats: torch.Tensor) -> torch.Tensor:
     return lr.reshape(b, 128, HIDDEN)
 
 
-def resolution_attention_v3(sd, lr: torch.Tensor, hr: torch.Tensor, prefix="resolution_attention"):
+def resolution_attention_v3(sd, lr: torch.Tensor, hr: torch.Tensor, prefix="resolution_attention", drop=None):
     """resolution_attention_v3.forward, spatial_pooling_projector.py:62-83 with kernel (1,4,4):
     each of the 128 pooled tokens attends (single head, d_k = 768) to its own 16 HR tokens;
     output_linear; LayerNorm(Wq(LR) + out)."""
@@ -222,18 +229,21 @@ def resolution_attention_v3(sd, lr: torch.Tensor, hr: torch.Tensor, prefix="reso
     q = _lin(lr.reshape(b, 128, 1, HIDDEN), sd, prefix + ".Wq")
     k = _lin(hr_win, sd, prefix + ".Wk")
     v = _lin(hr_win, sd, prefix + ".Wv")
-    x, _ = single_head_attention(q, k, v)
+    # train mode (drop = (mask [B,128,16], mask [B,128,768])): dropout on the probabilities (:76) and dropout_2 (:78)
+    x, _ = single_head_attention(q, k, v, None if drop is None else drop[0].reshape(b, 128, 1, 16))
     x = x.reshape(b, 128, HIDDEN)
     q = q.reshape(b, 128, HIDDEN)
     x = _lin(x, sd, prefix + ".output_linear")
+    if drop is not None:
+        x = x * drop[1]
     return _ln(q + x, sd, prefix + ".norm")
 
 
-def visual_packer(sd, feats: torch.Tensor) -> torch.Tensor:
+def visual_packer(sd, feats: torch.Tensor, drop=None) -> torch.Tensor:
     """VisualPacker_3d_phi_v3.forward, spatial_pooling_projector.py:138-146 -> [B,128,out_dim]."""
     feats = feats.float()
     lr = packer_pool(feats)
-    a = resolution_attention_v3(sd, lr, feats)
+    a = resolution_attention_v3(sd, lr, feats, drop=drop)
     h = F.gelu(_lin(a, sd, "proj_mpls.0"))
     return _lin(h, sd, "proj_mpls.2")
 

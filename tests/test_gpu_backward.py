@@ -206,15 +206,118 @@ def test_clip_stage1_training_step_smoke(cuda):
         loss.backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
 
 
-def test_train_mode_dropout_is_rejected_not_ignored(cuda):
+def _masks(drop, shapes, cuda):
+    """The keep masks the kernels applied for this forward (hsenet_dropout_mask), on the CPU for the oracle."""
+    from hsenet_b200 import training as tr
+    assert drop is not None
+    return (tr.dropout_mask(drop.p_attn, drop.seed_attn, shapes[0], cuda).cpu(),
+            tr.dropout_mask(drop.p_out, drop.seed_out, shapes[1], cuda).cpu())
+
+
+def test_dropout_mask_statistics(cuda):
+    """Counter-based keep mask: values in {0, 1/(1-p)}, keep rate 1-p, different seeds decorrelated, same seed repeatable,
+    p = 0 -> all ones."""
+    from hsenet_b200 import training as tr
+    n = 1 << 20
+    for p in (0.1, 0.5):
+        m = tr.dropout_mask(p, 1234, (n,), cuda)
+        vals = torch.unique(m)
+        assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.0 / (1.0 - p)) < 1e-6
+        keep = float((m > 0).float().mean())
+        assert abs(keep - (1.0 - p)) < 4.0 * (p * (1 - p) / n) ** 0.5 + 1e-4, (p, keep)
+        assert torch.equal(m, tr.dropout_mask(p, 1234, (n,), cuda))
+        m2 = tr.dropout_mask(p, 1235, (n,), cuda)
+        both = float(((m > 0) & (m2 > 0)).float().mean())
+        assert abs(both - (1.0 - p) ** 2) < 5e-3, (p, both)
+        # no structure along rows of 32 / 768 (the shapes the kernels index)
+        assert abs(float((m.view(-1, 32)[:, 0] > 0).float().mean()) - (1.0 - p)) < 2e-2
+    assert bool((tr.dropout_mask(0.0, 7, (1000,), cuda) == 1.0).all())
+
+
+@pytest.mark.parametrize("prec", ["fp32_verify", "bf16"])
+def test_packer_train_mode_dropout(cuda, prec):
+    """train() mode: Dropout(p=0.1) on the window-attention probabilities and on output_linear's result
+    (spatial_pooling_projector.py:58-59, 76-78) is applied by the kernels; forward and every gradient match the oracle run
+    with the SAME keep masks.  A second forward draws new masks; eval() is unchanged."""
     import hsenet_b200 as H
-    p = H.VisualPacker_3d_phi_v3((32, 256, 256), (4, 16, 16), 768, 3072, "mlp", 2).to(cuda).train()
-    x = torch.randn(1, 2048, 768, device=cuda)
-    with pytest.raises(NotImplementedError):
-        p(x)
-    y = p.disable_dropout()(x)
-    assert y.requires_grad
+    torch.manual_seed(3)
+    p = randomize_params(H.VisualPacker_3d_phi_v3((32, 256, 256), (4, 16, 16), 768, 3072, "mlp", 2))
+    sd = cpu_state(p)
+    feats = torch.randn(2, 2048, 768, generator=torch.Generator().manual_seed(9))
+    p = p.to(cuda).train()
+    assert p._dropout_active()
+    act = torch.float32 if prec == "fp32_verify" else torch.bfloat16
+    x = feats.to(cuda).to(act).requires_grad_(True)
+    torch.manual_seed(77)
+    with H.precision(prec):
+        y = p(x)
+    drop = p.last_dropout
+    assert abs(drop.p_attn - 0.1) < 1e-7 and abs(drop.p_out - 0.1) < 1e-7 and drop.seed_attn != drop.seed_out
+    masks = _masks(drop, ((2, 128, 16), (2, 128, 768)), cuda)
+    assert 0.8 < float((masks[0] > 0).float().mean()) < 0.97
+    fr = feats.clone().requires_grad_(True)
+    (cot,), ref, (ref_dhr,) = _oracle_grads(lambda s, f: O.visual_packer(s, f, drop=masks), sd, fr, seed=5)
+    ref_y = O.visual_packer(sd, feats, drop=masks)
+    m = metrics(y, ref_y)
+    assert (m["max_rel"] <= FP32_TOL) if prec == "fp32_verify" else (m["cos"] >= BF16_COS), m
+    no_drop = metrics(y, O.visual_packer(sd, feats))
+    assert no_drop["max_rel"] > 1e-2, no_drop            # the masks really changed the result
+    (y.float() * cot.to(cuda)).sum().backward()
+    print(prec, "packer train-mode grads", _check_grads(p, ref, prec))
+    m = metrics(x.grad, ref_dhr)
+    assert (m["max_rel"] <= FP32_TOL) if prec == "fp32_verify" else (m["cos"] >= BF16_COS), m
+    with H.precision(prec), torch.no_grad():
+        y2 = p(x)                                          # train() without grad: still dropout, new masks
+        assert p.last_dropout.seed_attn != drop.seed_attn
+        assert not torch.equal(y2, y.detach())
+        out = torch.empty(2, 128, 3072, dtype=act, device=cuda)
+        with pytest.raises(RuntimeError):
+            p.forward_into(x.detach(), out, 0)             # the raw-pointer inference path refuses to skip dropout
+        p.eval()
+        ye = p(x)
+    me = metrics(ye, O.visual_packer(sd, feats))
+    assert (me["max_rel"] <= FP32_TOL) if prec == "fp32_verify" else (me["cos"] >= BF16_COS), me
+    # same torch seed -> same masks -> same bits
+    p.train()
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(5)
+        with H.precision(prec), torch.no_grad():
+            outs.append(p(x).clone())
+    assert torch.equal(outs[0], outs[1])
+    assert p.disable_dropout()._dropout_active() is False
+
+
+@pytest.mark.parametrize("prec", ["fp32_verify", "bf16"])
+def test_vit_stage2_train_mode_dropout(cuda, prec):
+    """ViT_stage2.train(): the two Dropout(p=0.1) of slice_guided_attention (vit.py:46-47, 60-62) inside the kernels; output
+    and gradients against the oracle with the same masks."""
+    import hsenet_b200 as H
+    torch.manual_seed(2)
+    m = randomize_params(H.ViT_stage2(num_layers=1, **GEOM))
+    with torch.no_grad():
+        m.patch_score_proj.weight.mul_(8.0)              # informative gate (default init gives scores ~0.5)
+    sd = cpu_state(m)
+    B = 2
+    x, s = synthetic_inputs(B, seed=21)
+    m = m.to(cuda).train()
+    torch.manual_seed(123)
+    with H.precision(prec):
+        y, _ = m(x.to(cuda), s.to(cuda))
+    masks = _masks(m.last_dropout, ((B, 2048, 32), (B, 2048, 768)), cuda)
+    fn = lambda sd_, x_, s_: O.vit_stage2(sd_, x_, s_, drop=masks)[0]
+    cots, ref, _ = _oracle_grads(fn, sd, x, s, seed=11)
+    ref_y = O.vit_stage2(sd, x, s, drop=masks)[0]
+    mm = metrics(y, ref_y)
+    assert (mm["max_rel"] <= FP32_TOL) if prec == "fp32_verify" else (mm["cos"] >= BF16_COS), mm
+    ref_scores, _ = O.patch_scores(sd, O.patch_embedding(sd, x), s, drop=masks)
+    plain_scores, _ = O.patch_scores(sd, O.patch_embedding(sd, x), s)
+    ms = metrics(m.last_scores, ref_scores)
+    assert ms["max_rel"] <= (FP32_TOL if prec == "fp32_verify" else 2e-2), ms
+    assert metrics(m.last_scores, plain_scores)["max_rel"] > 10 * ms["max_rel"]      # dropout moved the scores
+    (y.float() * cots[0].to(cuda)).sum().backward()
+    print(prec, "stage2 train-mode grads", _check_grads(m, ref, prec))

@@ -169,10 +169,11 @@ def test_no_cpu_path_and_errors(cuda):
     # grad enabled + trainable parameters: the training path (row f-1) -- never a silent detach
     y, _ = m(torch.zeros(1, 1, 32, 256, 256, device=cuda))
     assert y.requires_grad and y.grad_fn is not None
-    # train-mode dropout of the slice-guided attention is rejected, not ignored (hsenet_b200/training.py)
+    # train-mode dropout of the slice-guided attention: applied by the training kernels, also without grad
     m2 = _build(H.ViT_stage2, 1).to(cuda).train()
-    with pytest.raises(NotImplementedError):
+    with torch.no_grad():
         m2(torch.zeros(1, 1, 32, 256, 256, device=cuda), torch.zeros(1, 32, 768, device=cuda))
+    assert m2.last_dropout is not None and abs(m2.last_dropout.p_attn - 0.1) < 1e-7
 
 
 def test_splice_into_llm_embeddings(cuda):

@@ -250,9 +250,11 @@ def test_dual_tower_two_stream_path_plumbing(monkeypatch):
     assert log == [("wait", "side", "cur"), ("prepare", 1, "side", False), ("prepare", 2, "cur", True),
                    ("wait", "cur", "side"), ("wait", "side", "cur"), ("replay", 1, "side"), ("replay", 2, "cur"),
                    ("wait", "cur", "side"), ("finish", 1, "cur"), ("finish", 2, "cur")]
+    # train() mode with dropout: the tower leaves the graph path (the training kernels apply dropout)
+    assert not tw.vision_tower_stage2._dropout_active()
     tw.vision_tower_stage2.train()
-    with pytest.raises(NotImplementedError):
-        tw._forward_concurrent(torch.zeros(1, 1, 32, 256, 256), torch.zeros(1, 32, 768))
+    assert tw.vision_tower_stage2._dropout_active() and not tw.vision_tower_stage1._dropout_active()
+    assert not tw.vision_tower_stage2.disable_dropout()._dropout_active()
 
 
 def test_preprocess_host_logic():

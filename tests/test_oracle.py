@@ -130,6 +130,54 @@ def test_restatement_vs_reference_live():
     assert tower.hidden_size == 768
 
 
+class _MaskDropout(torch.nn.Module):
+    """Stand-in for an nn.Dropout member of the reference module: multiplies by a preset keep mask."""
+
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, x):
+        return x * self.mask.reshape(x.shape)
+
+
+@needs_ref
+def test_train_mode_restatement_vs_reference_live():
+    """The oracle's ``drop=`` restatement of train mode (dropout on the probabilities, vit.py:31-32 /
+    spatial_pooling_projector.py:14-15, and dropout_2 in front of the residual, vit.py:62 / :78) against the reference's own
+    modules in .train() with their two nn.Dropout members replaced by the same explicit masks -- outputs and gradients."""
+    with RL.quiet():
+        vit, pk = RL.vit(), RL.packer()
+        torch.manual_seed(0)
+        m2 = vit.ViT_stage2(num_layers=1, **GEOM).train()
+        p = pk.VisualPacker_3d_phi_v3((32, 256, 256), (4, 16, 16), 768, 3072, "mlp", 2).train()
+    g = torch.Generator().manual_seed(3)
+    keep = lambda shape: (torch.rand(shape, generator=g) < 0.9).float() / 0.9
+    x, s = recipe_inputs(1, seed=5)
+    masks = (keep((1, 2048, 32)), keep((1, 2048, 768)))
+    a = m2.slice_guided_attention
+    a.dropout, a.dropout_2 = _MaskDropout(masks[0]), _MaskDropout(masks[1])
+    r2, _ = m2(x, s)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m2.state_dict().items()}
+    o2, _ = O.vit_stage2(sd, x, s, drop=masks)
+    assert metrics(o2.detach(), r2.detach())["max_rel"] < 1e-6
+    assert metrics(O.vit_stage2(sd, x, s)[0].detach(), r2.detach())["max_rel"] > 1e-3     # the masks matter
+    cot = torch.randn(r2.shape, generator=g)
+    (r2 * cot).sum().backward()
+    (o2 * cot).sum().backward()
+    for name, prm in m2.named_parameters():
+        ref_g, got = prm.grad, sd[name].grad
+        if ref_g is None or float(ref_g.abs().max()) < 1e-7:      # e.g. the key bias (cancels in the softmax)
+            assert got is None or float(got.abs().max()) < 1e-5, name
+            continue
+        assert metrics(got, ref_g)["max_rel"] < 1e-4, name
+    feats = torch.randn(1, 2048, 768, generator=g)
+    pm = (keep((1, 128, 16)), keep((1, 128, 768)))
+    ra = p.resolution_attention
+    ra.dropout, ra.dropout_2 = _MaskDropout(pm[0]), _MaskDropout(pm[1])
+    assert metrics(O.visual_packer(p.state_dict(), feats, drop=pm).detach(), p(feats).detach())["max_rel"] < 1e-5
+
+
 @needs_ref
 def test_gather_features_reference_single_process():
     """The reference's gather_features on a 1-process gloo group returns its inputs (dist_utils.py:292-293)."""

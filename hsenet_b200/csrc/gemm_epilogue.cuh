@@ -111,38 +111,41 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_ln_load(const GemmEpilogue& ep, int row_base, int M, int lane, float2 (&sq)[8]) {
   if constexpr (MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN) {
 #pragma unroll
-    // the 8 lanes that share a readback row each fetch ONE column-slab partial of it (slot = lane & 7)
-    for (int it = 0; it < 8; ++it) {
-      const int row = row_base + (lane >> 3) + 4 * it;
-      sq[it] = make_float2(0.f, 0.f);
-      if (row < M && (lane & 7) < ep.stats_slots) sq[it] = ep.stats_in[static_cast<long>(lane & 7) * ep.ld_stats + row];
+    // lane l fetches the (<= 8) column-slab partials of ITS row of the slab, row_base + l
+    const int row = row_base + lane;
+    for (int s = 0; s < 8; ++s) {
+      sq[s] = make_float2(0.f, 0.f);
+      if (row < M && s < ep.stats_slots) sq[s] = ep.stats_in[static_cast<long>(s) * ep.ld_stats + row];
     }
   }
 }
+// ln_a / ln_b come back as packed (value, value) pairs for the f32x2 FMAs of the readback: entry `it` belongs to row
+// row_base + (lane >> 3) + 4 * it.
 template <int MODE>
-__device__ __forceinline__ void epilogue_ln_coeffs(const GemmEpilogue& ep, const float2 (&sq)[8], float (&ln_a)[8],
-                                                   float (&ln_b)[8]) {
+__device__ __forceinline__ void epilogue_ln_coeffs(const GemmEpilogue& ep, const float2 (&sq)[8], int lane,
+                                                   uint64_t (&ln_a)[8], uint64_t (&ln_b)[8]) {
   if constexpr (MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN) {
+    float sx = 0.f, sy = 0.f;                    // slots in index order: the same bits every run
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { sx += sq[s].x; sy += sq[s].y; }
+    const float mean = sx * ep.ln_inv_dim;
+    const float var = fmaxf(sy * ep.ln_inv_dim - mean * mean, 0.f);
+    const float a = rsqrtf(var + ep.ln_eps);     // of row row_base + lane
+    const float b = -mean * a;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      float sx = sq[it].x, sy = sq[it].y;        // butterfly over the 8 slot lanes: same bits on every lane, every run
-#pragma unroll
-      for (int d = 1; d < 8; d <<= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, d);
-        sy += __shfl_xor_sync(0xffffffffu, sy, d);
-      }
-      const float mean = sx * ep.ln_inv_dim;
-      const float var = fmaxf(sy * ep.ln_inv_dim - mean * mean, 0.f);
-      ln_a[it] = rsqrtf(var + ep.ln_eps);
-      ln_b[it] = -mean * ln_a[it];
+      const int src = (lane >> 3) + 4 * it;
+      const float ai = __shfl_sync(0xffffffffu, a, src), bi = __shfl_sync(0xffffffffu, b, src);
+      ln_a[it] = pack2(ai, ai);
+      ln_b[it] = pack2(bi, bi);
     }
   }
 }
 
 template <int MODE, typename Release>
 __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t taddr, uint32_t stage, int row_base,
-                                              int col_base, int M, int N, int lane, const float (&ln_a)[8],
-                                              const float (&ln_b)[8], Release&& release) {
+                                              int col_base, int M, int N, int lane, const uint64_t (&ln_a)[8],
+                                              const uint64_t (&ln_b)[8], Release&& release) {
   const int sub_row = lane >> 3;         // 0..3   readback: 4 rows per pass
   const int sub_chunk = lane & 7;        // 16-byte column chunk owned by this lane in the readback
   const uint32_t wr_base = stage + lane * 128;
@@ -150,10 +153,10 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
   constexpr bool LN_IN = MODE == EPI_BF16_LN || MODE == EPI_BF16_GELU_LN;
   constexpr bool LN_OUT = MODE == EPI_F32_RESID_LN;
   // per-lane rows of the readback are row_base + sub_row + 4*it
-  float st_s[LN_OUT ? 8 : 1], st_q[LN_OUT ? 8 : 1];      // producer: partial sum / sum of squares over this slab
+  uint64_t st_s[LN_OUT ? 8 : 1], st_q[LN_OUT ? 8 : 1];   // producer: packed (even, odd column) partial sum / sum of squares
   if constexpr (LN_OUT) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) st_s[it] = st_q[it] = 0.f;
+    for (int it = 0; it < 8; ++it) st_s[it] = st_q[it] = pack2(0.f, 0.f);
   }
   // residual modes: the residual of chunk c+1 is requested before chunk c is processed (different addresses from the
   // stores of chunk c, so the in-place update stays safe); otherwise every chunk exposes a full HBM/L2 round trip
@@ -209,11 +212,9 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + sub_row;
         float4 x = lds128(rd_base + it * 512 + ((sub_chunk ^ (r & 7)) << 4));
-        if constexpr (LN_IN) {
-          x.x = fmaf(x.x, ln_a[it], fmaf(ln_b[it], cs4.x, bias4.x));
-          x.y = fmaf(x.y, ln_a[it], fmaf(ln_b[it], cs4.y, bias4.y));
-          x.z = fmaf(x.z, ln_a[it], fmaf(ln_b[it], cs4.z, bias4.z));
-          x.w = fmaf(x.w, ln_a[it], fmaf(ln_b[it], cs4.w, bias4.w));
+        if constexpr (LN_IN) {      // y = rstd x + (-mean rstd) colsum + bias', two columns per f32x2 FMA
+          unpack2(fma2(pack2(x.x, x.y), ln_a[it], fma2(ln_b[it], pack2(cs4.x, cs4.y), pack2(bias4.x, bias4.y))), x.x, x.y);
+          unpack2(fma2(pack2(x.z, x.w), ln_a[it], fma2(ln_b[it], pack2(cs4.z, cs4.w), pack2(bias4.z, bias4.w))), x.z, x.w);
         } else {
           x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
         }
@@ -253,8 +254,9 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
             pk.x = pack_bf16x2(x.x, x.y);
             pk.y = pack_bf16x2(x.z, x.w);
             *reinterpret_cast<uint2*>(ob + it * bstep) = pk;
-            st_s[it] += (x.x + x.y) + (x.z + x.w);
-            st_q[it] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+            const uint64_t xy = pack2(x.x, x.y), zw = pack2(x.z, x.w);
+            st_s[it] = add2(st_s[it], add2(xy, zw));
+            st_q[it] = fma2(zw, zw, fma2(xy, xy, st_q[it]));
           }
         }
       }
@@ -316,7 +318,13 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
     // 48-shuffle butterfly); lane (b2 b1 b0) ends up with the totals of row `it` = 4*b2 + 2*b1 + b0 and adds them.
     float v[16];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) { v[2 * it] = st_s[it]; v[2 * it + 1] = st_q[it]; }
+    for (int it = 0; it < 8; ++it) {
+      float lo, hi;
+      unpack2(st_s[it], lo, hi);
+      v[2 * it] = lo + hi;
+      unpack2(st_q[it], lo, hi);
+      v[2 * it + 1] = lo + hi;
+    }
     const bool b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
     float w8[8], w4[4], w2[2];
 #pragma unroll

@@ -158,8 +158,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
-      float ln_a[8], ln_b[8];
-      epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
+      uint64_t ln_a[8], ln_b[8];
+      epilogue_ln_coeffs<MODE>(ep, ln_sq, lane, ln_a, ln_b);                    // statistics requested one tile ago
       if (tile + tile_step < total_tiles)
         epilogue_ln_load<MODE>(ep, next_m0(tile + tile_step) + quarter * 32, M, lane, ln_sq);
       gwait(&bars->tmem_full[acc], acc_phase);

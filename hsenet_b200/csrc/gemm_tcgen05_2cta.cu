@@ -112,6 +112,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 }
 
 template <int MODE>
+// (10 warps on 4 schedulers = 3 warps on the fullest one: 16384 / 96 threads = 170 registers is the real ceiling, which is
+// what ptxas derives from the launch bounds -- __maxnreg__(200) compiles but cannot launch.)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const GemmEpilogue ep_in, int M, int N, int K, int ksplit, int kb_per, long split_stride) {
@@ -235,8 +237,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int n0 = (mn % n_tiles) * PN;
       GemmEpilogue ept = ep_in;                 // split-K: slice ks writes its own fp32 partial
       if (ksplit > 1) ept.out_f32 = ep_in.out_f32 + ks * split_stride;
-      float ln_a[8], ln_b[8];
-      epilogue_ln_coeffs<MODE>(ep, ln_sq, ln_a, ln_b);                    // statistics requested one tile ago
+      uint64_t ln_a[8], ln_b[8];
+      epilogue_ln_coeffs<MODE>(ep, ln_sq, lane, ln_a, ln_b);                    // statistics requested one tile ago
       if (tile + tile_step < total_tiles)
         epilogue_ln_load<MODE>(ep, next_m0(tile + tile_step) + quarter * 32, M, lane, ln_sq);
       gwait(&bars->tmem_full[acc], acc_phase);

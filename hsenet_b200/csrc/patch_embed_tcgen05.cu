@@ -182,7 +182,7 @@ patch_embed_tf32_kernel(const __grid_constant__ CUtensorMap tmVol, const __grid_
     const uint32_t stage = smem_epi + ew * EPI_WARP_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const float ln_a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ln_b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint64_t ln_a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ln_b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;

@@ -122,7 +122,7 @@ __device__ unsigned long long g_att_trace[48];   // [0,16) softmax warp 2, [16,3
     g_att_trace[(base) + 14] = clock64() - tstart;                                     \
     g_att_trace[(base) + 15] = nsub;                                                   \
   }
-__device__ long long g_att_times[12][48];         // rows 0..7: p_full arrive of softmax warp r; 8: s_full seen (warp 3); 9: issuer woken; 10: issue end; 11: issuer has its K/V operands
+__device__ long long g_att_times[14][48];         // rows 0..7: p_full arrive of softmax warp r; 8: s_full seen (warp 3); 9: issuer woken; 10: issue end; 11: issuer has its K/V operands; 12: top of the issuer step; 13: after the v_full wait
 #define ATT_TS(row, step)                                                                          \
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (step) < 48) g_att_times[row][step] = clock64()
 #define ATT_TV(row, step, val)                                                                     \
@@ -630,7 +630,9 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       ATT_TR_DECL;
       for (int t = 0; t < nsub; ++t) {
         const int sub = t & 1, j = t >> 1, vs = j % V_STAGES, t2 = t + 2;
+        if (lane == 0) { ATT_TS(12, t); }
         ctl_wait(&bars->v_full[vs], (j / V_STAGES) & 1);
+        if (lane == 0) { ATT_TS(13, t); }
         if (t2 < nsub) ctl_wait(&bars->k_full[(t2 >> 1) % K_STAGES], ((t2 >> 1) / K_STAGES) & 1);
         ATT_TR(0);
         if (lane == 0) { ATT_TS(11, t); }
@@ -1003,8 +1005,8 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, flo
 }  // namespace hs
 
 #ifdef HSENET_ATT_TRACE
-extern "C" int hsenet_debug_att_times(long long* host576) {
-  return cudaMemcpyFromSymbol(host576, hs::g_att_times, sizeof(long long) * 576) == cudaSuccess ? 0 : -4;
+extern "C" int hsenet_debug_att_times(long long* host672) {
+  return cudaMemcpyFromSymbol(host672, hs::g_att_times, sizeof(long long) * 672) == cudaSuccess ? 0 : -4;
 }
 extern "C" int hsenet_debug_att_trace(unsigned long long* host48) {
   return cudaMemcpyFromSymbol(host48, hs::g_att_trace, sizeof(unsigned long long) * 48) == cudaSuccess ? 0 : -4;

@@ -25,9 +25,9 @@ os.environ["HSENET_ATT_KERNEL"] = "split"
 for _ in range(3):
     lib.hsenet_self_attention(qkv.data_ptr(), out.data_ptr(), B, S, 0, st)
 torch.cuda.synchronize()
-buf = (C.c_longlong * 576)()
+buf = (C.c_longlong * 672)()
 assert fn(buf) == 0
-arr = [[buf[r * 48 + i] for i in range(48)] for r in range(12)]
+arr = [[buf[r * 48 + i] for i in range(48)] for r in range(14)]
 t0 = arr[8][2]
 print("CTA 0: issuing warp", arr[11][47], "(scheduler", arr[11][47] % 4, ")")
 print("step  s_full_seen | arrive of softmax warps 4..11 (scheduler = column % 4; rel. s_full_seen) | last arrive -> issuer woken   issue   issue_end -> s_full(t+2) | issuer: prev issue_end -> operands ready -> p_full seen")
@@ -36,4 +36,4 @@ for t in range(2, 31):
     arrives = [arr[r][t] - sf for r in range(8)]
     last = max(arr[r][t] for r in range(8))
     iw, ie, nxt = arr[9][t], arr[10][t], arr[8][t + 2]
-    print(f"{t:4d} {sf - t0:11d} | " + " ".join(f"{a:6d}" for a in arrives) + f" | {iw - last:10d} {ie - iw:14d} {nxt - ie:10d} | {arr[11][t] - arr[10][t - 1]:8d} {iw - arr[11][t]:8d}")
+    print(f"{t:4d} {sf - t0:11d} | " + " ".join(f"{a:6d}" for a in arrives) + f" | {iw - last:10d} {ie - iw:14d} {nxt - ie:10d} | {arr[11][t] - arr[10][t - 1]:8d} {iw - arr[11][t]:8d} | top {arr[12][t] - arr[10][t - 1]:5d} v_full {arr[13][t] - arr[12][t]:5d} k_full {arr[11][t] - arr[13][t]:5d}")

@@ -366,6 +366,9 @@ def main():
     n_sets = 4 if B <= 8 else 2                           # >= 268 MB of rotating inputs > 126 MB L2: inputs come from HBM
     host_sets = make_inputs(B, rank, n_sets, pinned=True)
     dev_sets = [(x.to(dev), s.to(dev)) for x, s in host_sets]
+    _t1 = getattr(getattr(enc, "vision_tower", None), "vision_tower_stage1", None)
+    if _t1 is not None:
+        config["layernorm_fold"] = bool(_t1.fold_layernorm)                                # HSENET_LN_FOLD (default on)
     config["l2_policy"] = (f"{n_sets} rotating input sets ({n_sets * B * 8.39:.0f} MB) + ~{B * 0.28:.1f} GB of "
                            "activations per step, both larger than the 126 MB L2; no explicit flush")
 

@@ -534,6 +534,10 @@ constexpr int ATS_THREADS = 384;   // four control warps (one per scheduler: pro
 // (Tried and removed: halving the commits per step -- K / V stages released once per 128-key tile, P V completion inferred
 // from s_full(t+1) -- made the kernel 3 % SLOWER and the issue burst longer, 350 -> 590 cycles: the issuing thread is held
 // by the tensor pipe's short queue, eight back-to-back MMAs block it longer than 4 + 4 with commits in between.)
+// (Tried and removed: computing the single live row of the 17th query tile (S = 2049 = 16 x 128 + 1, the cls row) on the
+// CUDA cores instead of running a whole tile CTA for it.  A tile CTA only lives ~27 us (147 us x 296 slots / 1632 CTAs); the
+// row path -- 2049 dot products, softmax, P V from L2 with 384 threads -- is bound by ~17 dependent L2 round trips and took
+// longer: 146.9 -> 154.8 us at batch 8, equal at batch 32.  S = 2048 measures 136 us: the 17th tile costs 8 %.)
 // (Tried and removed: pacing the issuing thread between MMAs.  An 80-cycle clock spin after each MMA removes the lag of the
 // issuer's scheduler mates completely -- all eight softmax warps then arrive within 150 cycles of each other -- but the
 // issuer itself becomes the limit (950 cycles per step, 176 us); 20-55 cycle pauses change nothing, 146.8 us.)

@@ -528,6 +528,9 @@ constexpr int ATS_THREADS = 384;   // four control warps (one per scheduler: pro
 // warp is moved), and p_full needs the slowest warp: the issue burst (8 tcgen05.mma + 4 commits, 350 cycles, held by the
 // tensor pipe's queue) starts exactly when those two warps begin their next step.  Spreading the two CTAs' issuers over
 // two schedulers does not remove that lag (each CTA still suffers from its own issuer) but measured +3 % at batch 32.
+#ifndef HSENET_ATT_OBSERVE_PV
+#define HSENET_ATT_OBSERVE_PV 1
+#endif
 #ifndef HSENET_ATT_SPREAD
 #define HSENET_ATT_SPREAD 1
 #endif
@@ -732,6 +735,14 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
                          row0 + j * KT, kEvictLast);
       }
       __syncwarp();
+      // This warp has slack: it also observes the P V completions of the previous tile's two steps, so that every phase of
+      // pv_done has a waiter before the barrier is committed again (compute-sanitizer synccheck's rule; the softmax warps
+      // only wait on it in the rare rescale path and at the end).  On the issuing warp the same wait cost 5 %.  The V stage
+      // this loop waits for next is released by the same two P V groups, so nothing is delayed.
+      if (kSingleIssuer && HSENET_ATT_OBSERVE_PV && j >= 1) {
+        ctl_wait(&bars->pv_done[0], (j - 1) & 1);
+        if (2 * (j - 1) + 1 < nsub) ctl_wait(&bars->pv_done[1], (j - 1) & 1);
+      }
     }
   } else if (warp == issuer_warp) {
     mma_issuer(0);

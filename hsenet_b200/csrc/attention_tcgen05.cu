@@ -541,6 +541,10 @@ constexpr int ATS_THREADS = 384;   // four control warps (one per scheduler: pro
 // CUDA cores instead of running a whole tile CTA for it.  A tile CTA only lives ~27 us (147 us x 296 slots / 1632 CTAs); the
 // row path -- 2049 dot products, softmax, P V from L2 with 384 threads -- is bound by ~17 dependent L2 round trips and took
 // longer: 146.9 -> 154.8 us at batch 8, equal at batch 32.  S = 2048 measures 136 us: the 17th tile costs 8 %.)
+// (Tried and removed: folding the orphan KEY (S % 64 == 1 costs every CTA a 33rd, masked step: 2.9 % by the S = 2048 / 2049
+// comparison) into the epilogue -- its score as a 64-long dot product on the CUDA cores, one more term in the merge of the key
+// halves.  Parity-green, 32 steps instead of 33, and slower in every placement tried: 148 -> 152-153 us at batch 8 with the
+// dot product in the epilogue (operands staged in shared memory) or before the loop (loads overlapping the pipeline fill).)
 // (Tried and removed: pacing the issuing thread between MMAs.  An 80-cycle clock spin after each MMA removes the lag of the
 // issuer's scheduler mates completely -- all eight softmax warps then arrive within 150 cycles of each other -- but the
 // issuer itself becomes the limit (950 cycles per step, 176 us); 20-55 cycle pauses change nothing, 146.8 us.)

@@ -30,7 +30,7 @@ def _attn_ref(qkv, B, S):
 
 
 @pytest.mark.parametrize("prec", [1, 0])
-@pytest.mark.parametrize("B,S", [(2, 2049), (2, 130), (3, 197), (1, 64), (1, 1)])
+@pytest.mark.parametrize("B,S", [(2, 2049), (2, 130), (3, 197), (1, 64), (1, 1), (2, 129)])
 def test_attention_backward(lib, cuda, B, S, prec):
     from hsenet_b200 import _lib
     g = torch.Generator().manual_seed(S * 7 + B)

@@ -161,7 +161,9 @@ def _attn_ref(qkv, B, S):
 @pytest.mark.parametrize("kernel", ["tri", "split", "rowwarp"])
 @pytest.mark.parametrize("B,S,scale", [(2, 2049, 1.0), (1, 2049, 4.0), (3, 128, 2.0), (2, 130, 1.0), (1, 1, 1.0),
                                        (1, 257, 8.0), (2, 66, 2.0), (1, 131, 1.0), (2, 192, 3.0), (1, 2050, 2.0),
-                                       (2, 33, 2.0), (1, 97, 1.0), (3, 31, 4.0), (5, 197, 2.0)])
+                                       (2, 33, 2.0), (1, 97, 1.0), (3, 31, 4.0), (5, 197, 2.0),
+                                       # S % 64 == 1: the split kernel folds the orphan key into its epilogue
+                                       (2, 129, 2.0), (1, 65, 1.0), (1, 193, 3.0)])
 def test_attention_bf16(lib, cuda, B, S, scale, kernel, monkeypatch):
     from hsenet_b200 import _lib
     monkeypatch.setenv("HSENET_ATT_KERNEL", kernel)      # read by the launcher on every call
@@ -179,7 +181,7 @@ def test_attention_bf16(lib, cuda, B, S, scale, kernel, monkeypatch):
 # Max-free softmax (scratch given): scale 0.4 keeps c |q| max|k| below the threshold (bounded mode), 1.0 mixes rows, 4.0
 # forces the exact fallback everywhere; anti-aligned and zero keys probe the underflow margin of the bound
 @pytest.mark.parametrize("B,S,scale", [(2, 2049, 0.4), (2, 2049, 1.0), (1, 2049, 4.0), (3, 197, 0.5), (2, 130, 0.3),
-                                       (1, 1, 0.5), (2, 33, 0.6), (1, 2050, 0.45)])
+                                       (1, 1, 0.5), (2, 33, 0.6), (1, 2050, 0.45), (2, 129, 0.4)])
 def test_attention_bf16_maxfree(lib, cuda, B, S, scale, monkeypatch):
     from hsenet_b200 import _lib
     monkeypatch.setenv("HSENET_ATT_MAXFREE", "1")        # opt-in mode (not faster on B200, kept with its tests)

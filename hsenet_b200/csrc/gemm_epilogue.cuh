@@ -30,6 +30,9 @@ namespace hs {
 enum : int { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_F32_RESID = 2, EPI_GENERIC = 3, EPI_BF16_LN = 4, EPI_BF16_GELU_LN = 5,
               EPI_F32_RESID_LN = 6 };
 
+#ifndef HSENET_EPI_PREFETCH
+#define HSENET_EPI_PREFETCH 1
+#endif
 constexpr int EPI_WARP_BYTES = 32 * 128;   // one 32x32 fp32 block per epilogue warp
 
 __host__ inline int epilogue_mode(const GemmEpilogue& ep) {
@@ -181,10 +184,13 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
     if (ep.bias != nullptr) bias_next = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
     if constexpr (LN_IN) cs_next = __ldg(reinterpret_cast<const float4*>(ep.colsum + c));
   };
+  // The accumulator chunk of step c+1 is requested from TMEM as soon as chunk c has been staged to shared memory (its
+  // registers are free again), so the TMEM round trip overlaps the readback / math / global stores of chunk c.
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
 #pragma unroll 1
   for (int chunk = 0; chunk < 4; ++chunk) {
-    uint32_t v[32];
-    tmem_ld32(taddr + chunk * 32, v);
+    if (!HSENET_EPI_PREFETCH && chunk > 0) tmem_ld32(taddr + chunk * 32, v);
     load_cols(chunk);
     const float4 bias4 = bias_next;
     [[maybe_unused]] const float4 cs4 = cs_next;
@@ -200,6 +206,7 @@ __device__ __forceinline__ void epilogue_slab(const GemmEpilogue& ep, uint32_t t
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       sts128(wr_base + ((c ^ wr_sw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    if (HSENET_EPI_PREFETCH && chunk < 3) tmem_ld32(taddr + (chunk + 1) * 32, v);
     __syncwarp();
     const int col = col_base + chunk * 32 + sub_chunk * 4;
     const int row_first = row_base + sub_row;            // rows row_first + 4*it

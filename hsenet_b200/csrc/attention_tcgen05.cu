@@ -48,10 +48,6 @@ constexpr int V_STAGES = HSENET_ATT_V_STAGES;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int SUB_BYTES = KS * 128;        // 64 rows x 128 B
 constexpr int ATT_THREADS = 224;   // producer warp, two MMA-issuing warps, four softmax warps
-#ifndef HSENET_ATT_EARLY_PROBE
-#define HSENET_ATT_EARLY_PROBE 0   // measured slower in both forms (register result: +4..9 %, deferred named predicate: +3..7 %)
-#endif
-constexpr bool kEarlyProbe = HSENET_ATT_EARLY_PROBE != 0;
 #ifndef HSENET_ATT_TRACE_WARP
 #define HSENET_ATT_TRACE_WARP 3
 #endif
@@ -63,27 +59,13 @@ constexpr bool kSingleIssuer = HSENET_ATT_SINGLE_ISSUER != 0;
 #define HSENET_ATT_PV_INTERLEAVE 1
 #endif
 constexpr bool kPvInterleave = HSENET_ATT_PV_INTERLEAVE != 0;
-// Split kernel: wait for / publish the P store of step t only after the score load of step t+1 has been issued.
-#ifndef HSENET_ATT_DEFER_ST
-#define HSENET_ATT_DEFER_ST 0
-#endif
-constexpr bool kDeferSt = HSENET_ATT_DEFER_ST != 0;
+// (Tried and removed: publishing the P store of step t only after the score load of step t+1 has been issued -- +4 %: the
+// p_full -> P V -> Q K^T -> s_full chain is on the cycle.)
 #ifndef HSENET_ATT_PARK
 #define HSENET_ATT_PARK 1
 #endif
-// Deferred mbarrier probe: the try_wait writes a NAMED PTX predicate (declared once per kernel by ATT_PROBE_DECL) and
-// returns immediately; the predicate is only read by att_probe_result() one step later, so the ~250-300 cycles a
-// (satisfied) probe takes to come back overlap the exponentials instead of sitting at the top of every step.
-#define ATT_PROBE_DECL asm volatile(".reg .pred att_pnext;\n\tsetp.ne.b32 att_pnext, 0, 0;" ::: "memory")
-__device__ __forceinline__ void att_probe_issue(uint64_t* bar, uint32_t parity) {
-  asm volatile("mbarrier.try_wait.parity.shared::cta.b64 att_pnext, [%0], %1;" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void att_probe_clear() { asm volatile("setp.ne.b32 att_pnext, 0, 0;" ::: "memory"); }
-__device__ __forceinline__ bool att_probe_result() {
-  uint32_t ok;
-  asm volatile("selp.b32 %0, 1, 0, att_pnext;" : "=r"(ok)::"memory");
-  return ok != 0;
-}
+// (Tried and removed: probing the NEXT step's s_full early -- result in a register: +4..9 %; deferred into a named PTX predicate
+// that is only read one step later: +3..7 %.)
 // waits of the producer / issuer warps (1 = parked try_wait with a suspend-time hint, 2 = also the softmax warps)
 __device__ __forceinline__ void ctl_wait(uint64_t* bar, uint32_t parity) {
   if (HSENET_ATT_PARK >= 1) mbar_wait_parked(bar, parity); else mbar_wait_nocall(bar, parity);
@@ -331,20 +313,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
     const float c = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
     float m = -INFINITY;                                 // running reference max (log2 domain, already scaled)
     float l = 0.f;
-    if constexpr (kEarlyProbe) ATT_PROBE_DECL;           // named predicate: result of the early probe of the NEXT step
     ATT_TR_DECL;
     // one 64-key step; MASKED (compile time) only for a last step that runs past the end of the sequence -- kept out
     // of the main loop on purpose: left as a run-time test the compiler turns the 64 per-key checks into selects that
     // execute on EVERY step (195 of ~530 instructions per step in the first version)
     auto softmax_step = [&](const int t, auto masked) {
       const int bsel = t % NBUF;
-      // S[bsel] ready and P[bsel] free.  The barrier was already probed during the previous step (below): even a
-      // satisfied mbarrier probe takes ~250-300 cycles to return, which is otherwise exposed at the top of every step.
-      if constexpr (kEarlyProbe) {
-        if (!att_probe_result()) smx_wait(&bars->s_full[bsel], (t / NBUF) & 1);
-      } else {
-        smx_wait(&bars->s_full[bsel], (t / NBUF) & 1);
-      }
+      // S[bsel] ready and P[bsel] free
+      smx_wait(&bars->s_full[bsel], (t / NBUF) & 1);
       tc_fence_after();
       ATT_TR(0);
       uint32_t x[64];
@@ -353,10 +329,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       if (warp_live) {
         tmem_ld32(tmem_base + lane_base + col_s(bsel), *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
         tmem_ld32(tmem_base + lane_base + col_s(bsel) + 32, *reinterpret_cast<uint32_t(*)[32]>(&x[32]));
-      }
-      if constexpr (kEarlyProbe) {
-        if (t + 1 < nsub) att_probe_issue(&bars->s_full[(t + 1) % NBUF], ((t + 1) / NBUF) & 1);
-        else att_probe_clear();
       }
       if (warp_live) tmem_ld_wait();
       ATT_TR(1);
@@ -788,17 +760,12 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       bounded = !__any_sync(0xffffffffu, !(mhat <= 50.0f));
       if (bounded) m = mhat;
     }
-    if constexpr (kEarlyProbe) ATT_PROBE_DECL;
     ATT_TR_DECL;
     auto softmax_step = [&](const int t, auto masked, auto maxfree) {
       constexpr bool MAXFREE = decltype(maxfree)::value;
       const int bsel = t & 1;
       const uint32_t col_s = ATS_COL_S + bsel * KS + half * 32;
-      if constexpr (kEarlyProbe) {
-        if (!att_probe_result()) smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
-      } else {
-        smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
-      }
+      smx_wait(&bars->s_full[bsel], (t >> 1) & 1);
       ATT_TR(0);
       if (warp == 4 && lane == 0) { ATT_TS(8, t); }
       tc_fence_after();
@@ -807,17 +774,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
       uint32_t pk[16];
       float alpha = 1.f;
       if (warp_live) tmem_ld32(tmem_base + lane_base + col_s, x);
-      if constexpr (kDeferSt) {
-        // the previous step's P store is only now waited for and published: its latency hides behind this step's
-        // barrier wait and score load instead of sitting on the warp's serial path
-        if (t > 0) {
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->p_full[bsel ^ 1]);
-        }
-      }
-      // (two buffers: s_full(t+1) completes while this step's exponentials run, so the probe is issued after them)
       if (warp_live) {
         tmem_ld_wait();
         ATT_TR(1);
@@ -872,10 +828,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         tmem_st16(tmem_base + lane_base + col_s, pk);
         ATT_TR(5);
       }
-      if constexpr (kEarlyProbe) {
-        if (t + 1 < nsub) att_probe_issue(&bars->s_full[bsel ^ 1], ((t + 1) >> 1) & 1);
-        else att_probe_clear();
-      }
       if (!MAXFREE && t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         smx_wait(&bars->pv_done[bsel ^ 1], ((t - 1) >> 1) & 1);
         if (t >= 2) smx_wait(&bars->pv_done[bsel], ((t >> 1) - 1) & 1);
@@ -891,12 +843,10 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16*
         }
       }
       ATT_TR(6);
-      if (!kDeferSt || t == nsub - 1) {
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
-      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
       if (lane == 0) { ATT_TS(warp - 4, t); }
       ATT_TR(7);
     };

@@ -424,23 +424,28 @@ def main():
         unfolded = None
         towers = (enc.vision_tower.vision_tower_stage1, enc.vision_tower.vision_tower_stage2)
         if rank == 0 and not args.no_extras and all(t.fold_layernorm for t in towers):
-            for tw in towers:
-                tw.fold_layernorm = False
-            KU = min(K, 5)
-            for i in range(2):
-                run_step(enc, args.workload, *dev_sets[i % n_sets])
-            lib.hsenet_profile_start()
-            for i in range(KU):
-                run_step(enc, args.workload, *dev_sets[i % n_sets])
-            ms_u = (C.c_double * NC)(); fl_u = (C.c_double * NC)(); by_u = (C.c_double * NC)(); ln_u = (C.c_uint64 * NC)()
-            _lib.check(lib.hsenet_profile_stop(ms_u, fl_u, by_u, ln_u), "profile_stop")
-            for tw in towers:
-                tw.fold_layernorm = True
-            g_tf = fl_u[0] / (ms_u[0] * 1e-3) / 1e12 if ms_u[0] > 0 else 0.0
-            unfolded = {"gemm_tflops": g_tf, "steps": KU,
-                        "share_ms": {"gemm": ms_u[0] / KU, "attention": ms_u[1] / KU, "layernorm": ms_u[2] / KU},
-                        "note": "same steps with HSENET_LN_FOLD=0 (every LayerNorm its own kernel): GEMM launches without "
-                                "the folded LayerNorm epilogue work"}
+            try:                                         # an extra record: it must never take the headline line down
+                for tw in towers:
+                    tw.fold_layernorm = False
+                KU = min(K, 5)
+                for i in range(2):
+                    run_step(enc, args.workload, *dev_sets[i % n_sets])
+                lib.hsenet_profile_start()
+                for i in range(KU):
+                    run_step(enc, args.workload, *dev_sets[i % n_sets])
+                ms_u = (C.c_double * NC)(); fl_u = (C.c_double * NC)(); by_u = (C.c_double * NC)(); ln_u = (C.c_uint64 * NC)()
+                _lib.check(lib.hsenet_profile_stop(ms_u, fl_u, by_u, ln_u), "profile_stop")
+                g_tf = fl_u[0] / (ms_u[0] * 1e-3) / 1e12 if ms_u[0] > 0 else 0.0
+                unfolded = {"gemm_tflops": g_tf, "steps": KU,
+                            "share_ms": {"gemm": ms_u[0] / KU, "attention": ms_u[1] / KU, "layernorm": ms_u[2] / KU},
+                            "note": "same steps with HSENET_LN_FOLD=0 (every LayerNorm its own kernel): GEMM launches "
+                                    "without the folded LayerNorm epilogue work"}
+            except Exception as exc:                     # noqa: BLE001
+                unfolded = None
+                sys.stderr.write(f"[bench] unfolded roofline pass skipped: {type(exc).__name__}: {exc}\n")
+            finally:
+                for tw in towers:
+                    tw.fold_layernorm = True
         for tw in towers:
             tw.use_cuda_graph = True
         enc.vision_tower.concurrent_towers = concurrent

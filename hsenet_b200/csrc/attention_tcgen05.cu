@@ -517,6 +517,9 @@ constexpr int ATS_THREADS = 384;   // four control warps (one per scheduler: pro
 // comparison) into the epilogue -- its score as a 64-long dot product on the CUDA cores, one more term in the merge of the key
 // halves.  Parity-green, 32 steps instead of 33, and slower in every placement tried: 148 -> 152-153 us at batch 8 with the
 // dot product in the epilogue (operands staged in shared memory) or before the loop (loads overlapping the pipeline fill).)
+// (Tried and archived as tools/attention_persist_experiment.cu.txt: a persistent grid over a work counter, producer and
+// issuer running ahead across tile boundaries so that the MMA pipeline never drains.  Parity-green, not faster: 168.6 us at
+// batch 8, 612 us at batch 32 -- the co-resident CTA already fills a CTA's prologue and epilogue.)
 // (Tried and removed: pacing the issuing thread between MMAs.  An 80-cycle clock spin after each MMA removes the lag of the
 // issuer's scheduler mates completely -- all eight softmax warps then arrive within 150 cycles of each other -- but the
 // issuer itself becomes the limit (950 cycles per step, 176 us); 20-55 cycle pauses change nothing, 146.8 us.)

@@ -77,9 +77,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken inside the host-time window [t0, t1] (the timed region; all samples if that window
+        caught none).  The sampler is started BEFORE the warm-up steps so that nvidia-smi's start-up (NVML init, ~0.1 s)
+        neither overlaps the timed steps nor contributes idle-clock samples."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +93,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= (t1 if t1 is not None else t))]
+        if not rows:
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -385,12 +391,12 @@ def main():
         return ms
 
     with torch.no_grad():
-        for i in range(W):
-            run_step(enc, args.workload, *dev_sets[i % n_sets])
-        barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for i in range(W):
+            run_step(enc, args.workload, *dev_sets[i % n_sets])
+        barrier()
         from hsenet_b200 import runtime as hrt
         launches0 = hrt.kernel_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -402,9 +408,10 @@ def main():
         e1.record()
         host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K
         barrier()
+        t_host1 = time.perf_counter()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = hrt.kernel_launch_count() - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(t_host0, t_host1 + 0.1) if rank == 0 else None
 
         # ---- roofline pass: the same K steps, instrumented with CUDA events around every launch of the library ----
         # (direct launches: the per-launch event hooks live in the library's launchers, which graph replays bypass)
